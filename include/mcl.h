@@ -1,0 +1,169 @@
+/*
+ * mcl.h -- C ABI of libmcl_sm100.so: the B200-native concept-embedding similarity scan.
+ *
+ * The reference (AskSid/multimodal_concept_learning) is pure Python and has no FFI of
+ * its own; the path is reached through ordinary Python calls into torch / sklearn /
+ * transformers.  Each entry point below therefore cites the *reference call site* whose
+ * arithmetic it replaces (paths relative to the reference tree).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless marked
+ *     "host"; sizes are in elements; matrices are row-major with the inner dim contiguous.
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates or frees device memory and never synchronises the stream.
+ *   - every call returns 0 on success or a negative MCL_ERR_* code; a message is kept in a
+ *     thread-local string readable with mcl_last_error().  No C++ exception crosses the ABI.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x the compute
+ *     calls return MCL_ERR_UNSUPPORTED_ARCH.
+ */
+#ifndef MCL_H_
+#define MCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCL_VERSION 100
+
+/* error codes */
+#define MCL_OK 0
+#define MCL_ERR_BAD_ARG (-1)
+#define MCL_ERR_UNALIGNED (-2)          /* base % 16 != 0 or ld*sizeof(elt) % 16 != 0 */
+#define MCL_ERR_UNSUPPORTED_ARCH (-3)   /* device is not sm_100 */
+#define MCL_ERR_WORKSPACE_TOO_SMALL (-4)
+#define MCL_ERR_CUDA (-5)
+#define MCL_ERR_NCCL (-6)
+#define MCL_ERR_UNIMPLEMENTED (-7)
+
+/* element types of q / table */
+#define MCL_DTYPE_BF16 0   /* product path: TMA + tcgen05 (UTCHMMA) + TMEM, fp32 accumulate */
+#define MCL_DTYPE_F32 1    /* check path: fp32 inputs, fp32 FMA accumulate on CUDA cores     */
+
+/* largest k the fused epilogue keeps per row */
+#define MCL_MAX_K 64
+
+/* row_stats layout: 4 floats per query row */
+#define MCL_STAT_M 0       /* max_j z_j                       */
+#define MCL_STAT_S 1       /* sum_j exp(z_j - m)              */
+#define MCL_STAT_SUMZ 2    /* sum_j z_j  (label smoothing)    */
+#define MCL_STAT_ZLABEL 3  /* z_label, 0 if ignored/not local */
+
+typedef void* mcl_stream_t; /* a cudaStream_t */
+
+int mcl_version(void);
+const char* mcl_last_error(void); /* host string, thread-local, valid until the next call */
+
+/* sm count and compute capability of the current device (host outputs). */
+int mcl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * inv_norm_out[i] = 1 / ||x[i,:]||_2 in fp32; rows with norm < 10*FLT_EPSILON give 1
+ * (scikit-learn `normalize` semantics).
+ * Replaces: the two sklearn `normalize` calls inside `cosine_similarity` at
+ *   src/multimodal/token_embedding_analysis.py:244, and the numpy row-normalisation of
+ *   random_experiments/multi_token_embedding/multi_token.ipynb cell 3 line 16.
+ */
+int mcl_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                     float* inv_norm_out, mcl_stream_t stream);
+
+/*
+ * Multi-token concept embeddings: out[i,:] = mean(table[ids[offsets[i]:offsets[i+1]], :]),
+ * empty segments give zeros; fp32 accumulation, one rounding to the table dtype; if
+ * `normalize` != 0 the mean is L2-normalised (fp32) before the rounding.
+ * Replaces: `average_embeddings_for_tokens`
+ *   src/multimodal/token_embedding_analysis_imagenet.py:261-286 (hot line :281) and
+ *   `get_averaged_embedding`, multi_token.ipynb cell 2 lines 1-12.
+ * ids outside [0,V) -> MCL_ERR_BAD_ARG is NOT detectable without a sync; they are clamped
+ * on the device and flagged in *bad_id_flag (device int, nullable).
+ */
+int mcl_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t ld,
+                    const int64_t* offsets /*[Q+1]*/, const int64_t* ids /*[nnz]*/, int64_t Q,
+                    int normalize, void* out /*[Q,D] table dtype*/, int64_t ld_out,
+                    int* bad_id_flag, mcl_stream_t stream);
+
+/*
+ * The fused scan.  For every query row i (z_ij = <q_i, t_j> * rq_i * rt_j * scale, with
+ * rq / rt the optional inverse row norms):
+ *     topk_val[i,:], topk_idx[i,:]  the k largest z_ij, descending, exact ties broken by
+ *                                   the lowest table row; idx = index_base + local row
+ *     row_stats[i,:]                (m, s, sum_z, z_label) -- see MCL_STAT_*
+ * The [Q x V] score matrix is never written to memory.  lse_i = m + log s;
+ * CE_i = (1-eps)(lse_i - z_label) + eps (lse_i - sum_z / V) is formed by the caller.
+ * Replaces, in one call:
+ *   - sklearn `cosine_similarity` per pair   src/multimodal/token_embedding_analysis.py:237-246
+ *   - HF lm_head GEMM + fp32 upcast + `F.cross_entropy(ignore_index=-100)`
+ *                                            src/multimodal/mllm.py:115-120
+ *   - `torch.argmax(logits, dim=-1)`         src/multimodal/multimodal_training.py:276
+ *   - `CrossEntropyLoss(label_smoothing)` + `torch.max(logits, 1)`
+ *                                            src/vision/vision_training.py:81-83,116,132
+ * Constraints: 1 <= k <= min(V_local, MCL_MAX_K); scale > 0; D % 8 == 0 (bf16) so rows are
+ * 16-byte aligned; bases 16-byte aligned.  labels are GLOBAL row ids (int64), -100 = ignore.
+ */
+size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, int dtype);
+
+int mcl_concept_scan(const void* q /*[Q,D]*/, const void* table /*[V_local,D]*/, int dtype,
+                     int64_t Q, int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                     const float* inv_norm_q /*[Q] nullable*/,
+                     const float* inv_norm_t /*[V_local] nullable*/, float scale, int k,
+                     int64_t index_base, const int64_t* labels /*[Q] nullable*/,
+                     float* topk_val /*[Q,k]*/, int64_t* topk_idx /*[Q,k]*/,
+                     float* row_stats /*[Q,4]*/, void* workspace, size_t workspace_bytes,
+                     mcl_stream_t stream);
+
+/* Same call, additionally dumping z to scores_out [Q, V_local] fp32 (tests only). */
+int mcl_concept_scan_debug(const void* q, const void* table, int dtype, int64_t Q,
+                           int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                           const float* inv_norm_q, const float* inv_norm_t, float scale, int k,
+                           int64_t index_base, const int64_t* labels, float* topk_val,
+                           int64_t* topk_idx, float* row_stats, void* workspace,
+                           size_t workspace_bytes, float* scores_out, mcl_stream_t stream);
+
+/*
+ * Merge R partial results (one per vocabulary shard): candidates are re-ranked by
+ * (value desc, index asc); m* = max m_r, s* = sum s_r exp(m_r - m*); sum_z and z_label add.
+ * val/idx/stats are [R,Q,k] / [R,Q,k] / [R,Q,4]; idx < 0 marks an empty candidate.
+ */
+int mcl_merge(const float* val, const int64_t* idx, const float* stats, int R, int64_t Q, int k,
+              float* out_val, int64_t* out_idx, float* out_stats, mcl_stream_t stream);
+
+/*
+ * Vocabulary-sharded scan over the GPUs of one NVSwitch box: local scan, ONE ncclAllGather
+ * of the packed per-rank record, local merge -- all enqueued on `stream`.
+ * The library owns only the communicator.  `unique_id` is the 128-byte ncclUniqueId (host),
+ * produced on rank 0 by mcl_comm_unique_id and distributed by the caller
+ * (torch.distributed's store in the Python host layer).
+ */
+int mcl_comm_unique_id(void* unique_id_out /*host, 128 B*/);
+int mcl_comm_init(const void* unique_id /*host, 128 B*/, int world, int rank, void** comm_out);
+int mcl_comm_destroy(void* comm);
+
+/* bytes of `gather_buf` needed by mcl_concept_scan_sharded */
+size_t mcl_sharded_gather_bytes(int64_t Q, int k, int world);
+
+int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, int64_t Q,
+                             int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                             const float* inv_norm_q, const float* inv_norm_t, float scale,
+                             int k, int64_t index_base, const int64_t* labels,
+                             float* topk_val, int64_t* topk_idx, float* row_stats,
+                             void* workspace, size_t workspace_bytes, void* gather_buf,
+                             size_t gather_bytes, void* comm, int world, int rank,
+                             mcl_stream_t stream);
+
+/*
+ * Tuning knobs (host-side, process-global).  opt: 0 = CTAs per launch (0 = all SMs),
+ * 1 = row-block group size g of the tile scheduler (0 = heuristic), 2 = route bf16 inputs
+ * through the CUDA-core check kernel instead of tcgen05 (tests only).  Returns the old value.
+ */
+int64_t mcl_set_option(int opt, int64_t value);
+
+/* number of kernel launches the library has enqueued in this process (for bench.py) */
+int64_t mcl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libmcl_sm100.so (include/mcl.h).  No torch types cross this layer:
+pointers are integers (``tensor.data_ptr()``), sizes are Python ints.
+
+There is deliberately no fallback: if the shared library is missing the import of any
+compute entry point raises, and every non-zero return code becomes an exception."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcl_sm100.so")
+
+MCL_DTYPE_BF16, MCL_DTYPE_F32 = 0, 1
+MCL_MAX_K = 64
+ERR_NAMES = {0: "OK", -1: "BAD_ARG", -2: "UNALIGNED", -3: "UNSUPPORTED_ARCH",
+             -4: "WORKSPACE_TOO_SMALL", -5: "CUDA", -6: "NCCL", -7: "UNIMPLEMENTED"}
+
+
+class MclError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmcl_sm100: MCL_ERR_{ERR_NAMES.get(code, code)} ({code}): {msg}")
+        self.code = code
+
+
+_i64, _i32, _f32, _ptr, _sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/mcl.h line by line
+SIGNATURES = {
+    "mcl_version": (_i32, []),
+    "mcl_last_error": (C.c_char_p, []),
+    "mcl_device_info": (_i32, [C.POINTER(_i32)] * 3),
+    "mcl_row_inv_norm": (_i32, [_ptr, _i32, _i64, _i64, _i64, _ptr, _ptr]),
+    "mcl_gather_mean": (_i32, [_ptr, _i32, _i64, _i64, _i64, _ptr, _ptr, _i64, _i32, _ptr, _i64,
+                               _ptr, _ptr]),
+    "mcl_scan_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
+    "mcl_concept_scan": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32,
+                                _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "mcl_concept_scan_debug": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
+                                      _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr,
+                                      _ptr]),
+    "mcl_merge": (_i32, [_ptr, _ptr, _ptr, _i32, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "mcl_comm_unique_id": (_i32, [_ptr]),
+    "mcl_comm_init": (_i32, [_ptr, _i32, _i32, C.POINTER(_ptr)]),
+    "mcl_comm_destroy": (_i32, [_ptr]),
+    "mcl_sharded_gather_bytes": (_sz, [_i64, _i32, _i32]),
+    "mcl_concept_scan_sharded": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
+                                        _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr,
+                                        _sz, _ptr, _i32, _i32, _ptr]),
+    "mcl_set_option": (_i64, [_i32, _i64]),
+    "mcl_launch_count": (_i64, []),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """dlopen the library and type every entry point; raises if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing. Build it with "
+                    "`python -m multimodal_concept_learning_b200.build` (needs nvcc). "
+                    "There is no CPU or PyTorch fallback for the concept scan.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)   # AttributeError if the .so does not export it
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return (load().mcl_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MclError(rc, last_error())

@@ -1,0 +1,378 @@
+// extern "C" surface of libmcl_sm100.so (include/mcl.h).  Argument checking, workspace
+// carving, kernel sequencing on the caller's stream, error strings, and the NCCL
+// communicator (resolved with dlopen so the library loads on machines without NCCL).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <mutex>
+#include "../../include/mcl.h"
+#include "kernels.h"
+
+using namespace mcl;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MCL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DevInfo { int sm = 0, major = 0, minor = 0; bool ok = false; };
+bool dev_info(DevInfo* out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  static std::mutex mu;
+  static DevInfo cache[64];
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 0 || dev >= 64) return false;
+  if (!cache[dev].ok) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return false;
+    cache[dev].sm = p.multiProcessorCount;
+    cache[dev].major = p.major;
+    cache[dev].minor = p.minor;
+    cache[dev].ok = true;
+  }
+  *out = cache[dev];
+  return true;
+}
+int require_sm100(DevInfo* d) {
+  if (!dev_info(d)) {
+    cudaGetLastError();
+    return fail(MCL_ERR_CUDA, "no usable CUDA device (libmcl_sm100 has no CPU fallback)");
+  }
+  if (d->major != 10)
+    return fail(MCL_ERR_UNSUPPORTED_ARCH, "device is sm_%d%d; libmcl_sm100 is built for sm_100a only",
+                d->major, d->minor);
+  return MCL_OK;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+size_t elt_size(int dtype) { return dtype == MCL_DTYPE_BF16 ? 2 : 4; }
+
+int simt_nsplit(int64_t Q, int64_t V, int sm) {
+  const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
+  const int num_chunks = (int)((V + kChunk - 1) / kChunk);
+  int ns = (4 * sm + num_rb - 1) / num_rb;
+  if (ns > num_chunks) ns = num_chunks;
+  if (ns < 1) ns = 1;
+  // no empty splits: chunks_per_split = ceil(chunks / ns), then ns = ceil(chunks / cps)
+  const int cps = (num_chunks + ns - 1) / ns;
+  return (num_chunks + cps - 1) / cps;
+}
+
+int scan_nslots(int64_t Q, int64_t V, int64_t D, int dtype, int sm, TcSchedule* sch_out,
+                int* nsplit_out) {
+  if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
+    TcSchedule s = make_tc_schedule(Q, V, D, sm, (int)g_opt_ctas.load(), (int)g_opt_g.load());
+    if (sch_out) *sch_out = s;
+    return s.grid * s.max_seg;
+  }
+  const int ns = simt_nsplit(Q, V, sm);
+  if (nsplit_out) *nsplit_out = ns;
+  return (int)((Q + kBlockM - 1) / kBlockM) * ns;
+}
+
+int check_scan_args(const void* q, const void* table, int dtype, int64_t Q, int64_t V, int64_t D,
+                    int64_t ldq, int64_t ldt, const float* inv_q, const float* inv_t, float scale,
+                    int k, const float* topk_val, const int64_t* topk_idx, const float* row_stats) {
+  if (dtype != MCL_DTYPE_BF16 && dtype != MCL_DTYPE_F32) return fail(MCL_ERR_BAD_ARG, "dtype %d", dtype);
+  if (Q < 0 || V < 1 || D < 1) return fail(MCL_ERR_BAD_ARG, "bad shape Q=%lld V=%lld D=%lld", (long long)Q, (long long)V, (long long)D);
+  if (Q >= (1ll << 31) || V >= (1ll << 31) || D >= (1ll << 31)) return fail(MCL_ERR_BAD_ARG, "shape exceeds 2^31");
+  if (k < 1 || k > MCL_MAX_K || k > V) return fail(MCL_ERR_BAD_ARG, "k=%d must be in [1, min(V=%lld, %d)]", k, (long long)V, MCL_MAX_K);
+  if (!(scale > 0.f) || !(scale < INFINITY)) return fail(MCL_ERR_BAD_ARG, "scale must be finite and > 0");
+  if (ldq < D || ldt < D) return fail(MCL_ERR_BAD_ARG, "ld < D");
+  if (Q > 0 && (!q || !topk_val || !topk_idx || !row_stats)) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  if (!table) return fail(MCL_ERR_BAD_ARG, "null table");
+  const size_t es = elt_size(dtype);
+  if (!aligned16(q) || !aligned16(table) || (ldq * es) % 16 || (ldt * es) % 16)
+    return fail(MCL_ERR_UNALIGNED, "q/table base and row pitch must be multiples of 16 bytes");
+  if ((inv_t && !aligned16(inv_t)) || !aligned16(row_stats))
+    return fail(MCL_ERR_UNALIGNED, "inv_norm_t / row_stats must be 16-byte aligned");
+  (void)inv_q;
+  return MCL_OK;
+}
+
+int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V, int64_t D,
+              int64_t ldq, int64_t ldt, const float* inv_q, const float* inv_t, float scale, int k,
+              int64_t index_base, const int64_t* labels, float* topk_val, int64_t* topk_idx,
+              float* row_stats, void* workspace, size_t workspace_bytes, float* dbg,
+              cudaStream_t stream) {
+  int rc = check_scan_args(q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, topk_val,
+                           topk_idx, row_stats);
+  if (rc) return rc;
+  DevInfo di;
+  if ((rc = require_sm100(&di))) return rc;
+  if (Q == 0) return MCL_OK;
+  TcSchedule sch{};
+  int nsplit = 1;
+  const int nslots = scan_nslots(Q, V, D, dtype, di.sm, &sch, &nsplit);
+  Workspace ws = carve_workspace(workspace, nslots);
+  if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
+    return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
+                workspace_bytes, ws.bytes);
+  ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg};
+  SlotMap sm{};
+  cudaError_t e;
+  if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
+    char msg[256] = "";
+    e = launch_scan_tc(a, sch, ws.sv, stream, msg, sizeof(msg));
+    if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);
+    sm.mode = 0; sm.g = sch.g; sm.jpg = sch.jpg; sm.num_vt = sch.num_vt; sm.max_seg = sch.max_seg;
+  } else {
+    e = launch_scan_simt(a, ws.sv, nsplit, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "scan_simt launch");
+    sm.mode = 1; sm.nsplit = nsplit;
+  }
+  g_launches++;
+  e = launch_merge_slots(ws.sv, sm, Q, k, inv_q, scale, index_base, topk_val, topk_idx, row_stats, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "merge launch");
+  g_launches++;
+  return MCL_OK;
+}
+
+// ---- NCCL through dlopen ---------------------------------------------------------------
+struct NcclUid { char internal[128]; };
+typedef int (*nccl_get_uid_t)(NcclUid*);
+typedef int (*nccl_init_rank_t)(void**, int, NcclUid, int);
+typedef int (*nccl_destroy_t)(void*);
+typedef int (*nccl_allgather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_t)(int);
+struct NcclApi {
+  void* h = nullptr;
+  nccl_get_uid_t get_uid = nullptr;
+  nccl_init_rank_t init_rank = nullptr;
+  nccl_destroy_t destroy = nullptr;
+  nccl_allgather_t allgather = nullptr;
+  nccl_errstr_t errstr = nullptr;
+};
+NcclApi* nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (!api.h) return;
+    api.get_uid = (nccl_get_uid_t)dlsym(api.h, "ncclGetUniqueId");
+    api.init_rank = (nccl_init_rank_t)dlsym(api.h, "ncclCommInitRank");
+    api.destroy = (nccl_destroy_t)dlsym(api.h, "ncclCommDestroy");
+    api.allgather = (nccl_allgather_t)dlsym(api.h, "ncclAllGather");
+    api.errstr = (nccl_errstr_t)dlsym(api.h, "ncclGetErrorString");
+  });
+  if (!api.h || !api.get_uid || !api.init_rank || !api.destroy || !api.allgather) return nullptr;
+  return &api;
+}
+int nccl_fail(NcclApi* n, int rc, const char* what) {
+  return fail(MCL_ERR_NCCL, "%s: %s", what, (n && n->errstr) ? n->errstr(rc) : "nccl error");
+}
+
+struct Record { size_t val_off, idx_off, stats_off, bytes; };
+Record record_layout(int64_t Q, int k) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  Record r;
+  r.val_off = 0;
+  r.idx_off = up((size_t)Q * k * 4);
+  r.stats_off = r.idx_off + up((size_t)Q * k * 8);
+  r.bytes = r.stats_off + up((size_t)Q * 16);
+  return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcl_version(void) { return MCL_VERSION; }
+const char* mcl_last_error(void) { return g_err; }
+
+int mcl_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  DevInfo d;
+  if (!dev_info(&d)) {
+    cudaGetLastError();
+    return fail(MCL_ERR_CUDA, "no usable CUDA device");
+  }
+  if (sm_count) *sm_count = d.sm;
+  if (cc_major) *cc_major = d.major;
+  if (cc_minor) *cc_minor = d.minor;
+  return MCL_OK;
+}
+
+int mcl_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                     float* inv_norm_out, mcl_stream_t stream) {
+  if (dtype != MCL_DTYPE_BF16 && dtype != MCL_DTYPE_F32) return fail(MCL_ERR_BAD_ARG, "dtype %d", dtype);
+  if (rows < 0 || dim < 1 || ld < dim) return fail(MCL_ERR_BAD_ARG, "bad shape rows=%lld dim=%lld ld=%lld", (long long)rows, (long long)dim, (long long)ld);
+  if (rows > 0 && (!x || !inv_norm_out)) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  if (!aligned16(x) || (ld * elt_size(dtype)) % 16) return fail(MCL_ERR_UNALIGNED, "x base and row pitch must be multiples of 16 bytes");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  cudaError_t e = launch_row_inv_norm(x, dtype, rows, dim, ld, inv_norm_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "row_inv_norm launch");
+  if (rows) g_launches++;
+  return MCL_OK;
+}
+
+int mcl_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t ld,
+                    const int64_t* offsets, const int64_t* ids, int64_t Q, int normalize, void* out,
+                    int64_t ld_out, int* bad_id_flag, mcl_stream_t stream) {
+  if (dtype != MCL_DTYPE_BF16 && dtype != MCL_DTYPE_F32) return fail(MCL_ERR_BAD_ARG, "dtype %d", dtype);
+  if (V < 1 || D < 1 || ld < D || ld_out < D || Q < 0) return fail(MCL_ERR_BAD_ARG, "bad shape");
+  if (!table || (Q > 0 && (!offsets || !out))) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  const size_t es = elt_size(dtype);
+  if (!aligned16(table) || !aligned16(out) || (ld * es) % 16 || (ld_out * es) % 16)
+    return fail(MCL_ERR_UNALIGNED, "table/out base and row pitch must be multiples of 16 bytes");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  cudaError_t e = launch_gather_mean(table, dtype, V, D, ld, offsets, ids, Q, normalize, out, ld_out,
+                                     bad_id_flag, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "gather_mean launch");
+  if (Q) g_launches++;
+  return MCL_OK;
+}
+
+size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, int dtype) {
+  (void)k;
+  DevInfo di;
+  if (!dev_info(&di)) { cudaGetLastError(); di.sm = 148; }
+  if (Q <= 0 || V_local <= 0 || D <= 0) return 256;
+  const int nslots = scan_nslots(Q, V_local, D, dtype, di.sm, nullptr, nullptr);
+  return carve_workspace(nullptr, nslots).bytes;
+}
+
+int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
+                     int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                     const float* inv_norm_t, float scale, int k, int64_t index_base,
+                     const int64_t* labels, float* topk_val, int64_t* topk_idx, float* row_stats,
+                     void* workspace, size_t workspace_bytes, mcl_stream_t stream) {
+  return scan_impl(q, table, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, k,
+                   index_base, labels, topk_val, topk_idx, row_stats, workspace, workspace_bytes,
+                   nullptr, (cudaStream_t)stream);
+}
+
+int mcl_concept_scan_debug(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
+                           int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                           const float* inv_norm_t, float scale, int k, int64_t index_base,
+                           const int64_t* labels, float* topk_val, int64_t* topk_idx,
+                           float* row_stats, void* workspace, size_t workspace_bytes,
+                           float* scores_out, mcl_stream_t stream) {
+  return scan_impl(q, table, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, k,
+                   index_base, labels, topk_val, topk_idx, row_stats, workspace, workspace_bytes,
+                   scores_out, (cudaStream_t)stream);
+}
+
+int mcl_merge(const float* val, const int64_t* idx, const float* stats, int R, int64_t Q, int k,
+              float* out_val, int64_t* out_idx, float* out_stats, mcl_stream_t stream) {
+  if (R < 1 || Q < 0 || k < 1 || k > MCL_MAX_K) return fail(MCL_ERR_BAD_ARG, "bad R/Q/k");
+  if (Q > 0 && (!val || !idx || !stats || !out_val || !out_idx || !out_stats)) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  if (!aligned16(stats) || !aligned16(out_stats)) return fail(MCL_ERR_UNALIGNED, "stats must be 16-byte aligned");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  cudaError_t e = launch_merge_ranks(val, idx, stats, (size_t)Q * k * 4, (size_t)Q * k * 8,
+                                     (size_t)Q * 16, R, Q, k, out_val, out_idx, out_stats,
+                                     (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "merge launch");
+  if (Q) g_launches++;
+  return MCL_OK;
+}
+
+int mcl_comm_unique_id(void* unique_id_out) {
+  NcclApi* n = nccl();
+  if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror() ? dlerror() : "");
+  if (!unique_id_out) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  int rc = n->get_uid((NcclUid*)unique_id_out);
+  if (rc) return nccl_fail(n, rc, "ncclGetUniqueId");
+  return MCL_OK;
+}
+
+int mcl_comm_init(const void* unique_id, int world, int rank, void** comm_out) {
+  NcclApi* n = nccl();
+  if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable");
+  if (!unique_id || !comm_out || world < 1 || rank < 0 || rank >= world) return fail(MCL_ERR_BAD_ARG, "bad comm args");
+  NcclUid uid;
+  memcpy(&uid, unique_id, sizeof(uid));
+  void* comm = nullptr;
+  int rc = n->init_rank(&comm, world, uid, rank);
+  if (rc) return nccl_fail(n, rc, "ncclCommInitRank");
+  *comm_out = comm;
+  return MCL_OK;
+}
+
+int mcl_comm_destroy(void* comm) {
+  NcclApi* n = nccl();
+  if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable");
+  if (!comm) return MCL_OK;
+  int rc = n->destroy(comm);
+  if (rc) return nccl_fail(n, rc, "ncclCommDestroy");
+  return MCL_OK;
+}
+
+size_t mcl_sharded_gather_bytes(int64_t Q, int k, int world) {
+  if (Q < 0 || k < 1 || world < 1) return 0;
+  return record_layout(Q, k).bytes * (size_t)world;
+}
+
+int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, int64_t Q,
+                             int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                             const float* inv_norm_q, const float* inv_norm_t, float scale, int k,
+                             int64_t index_base, const int64_t* labels, float* topk_val,
+                             int64_t* topk_idx, float* row_stats, void* workspace,
+                             size_t workspace_bytes, void* gather_buf, size_t gather_bytes,
+                             void* comm, int world, int rank, mcl_stream_t stream) {
+  if (world < 1 || rank < 0 || rank >= world) return fail(MCL_ERR_BAD_ARG, "bad world/rank");
+  const Record rec = record_layout(Q, k);
+  if (!gather_buf || gather_bytes < rec.bytes * (size_t)world || !aligned16(gather_buf))
+    return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "gather_buf %zu B < required %zu B", gather_bytes,
+                rec.bytes * (size_t)world);
+  char* mine = (char*)gather_buf + rec.bytes * (size_t)rank;
+  // 1. local scan straight into this rank's record of the gather buffer
+  int rc = scan_impl(q, table_shard, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale,
+                     k, index_base, labels, (float*)(mine + rec.val_off),
+                     (int64_t*)(mine + rec.idx_off), (float*)(mine + rec.stats_off), workspace,
+                     workspace_bytes, nullptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  // 2. one all-gather of the packed records (in place)
+  if (world > 1) {
+    NcclApi* n = nccl();
+    if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable");
+    if (!comm) return fail(MCL_ERR_BAD_ARG, "null communicator");
+    int nrc = n->allgather(mine, gather_buf, rec.bytes, /*ncclInt8*/ 0, comm, (cudaStream_t)stream);
+    if (nrc) return nccl_fail(n, nrc, "ncclAllGather");
+  }
+  // 3. merge the R records
+  char* base = (char*)gather_buf;
+  cudaError_t e = launch_merge_ranks((const float*)(base + rec.val_off),
+                                     (const int64_t*)(base + rec.idx_off),
+                                     (const float*)(base + rec.stats_off), rec.bytes, rec.bytes,
+                                     rec.bytes, world, Q, k, topk_val, topk_idx, row_stats,
+                                     (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "merge launch");
+  if (Q) g_launches++;
+  return MCL_OK;
+}
+
+int64_t mcl_set_option(int opt, int64_t value) {
+  if (opt == 0) return g_opt_ctas.exchange(value);
+  if (opt == 1) return g_opt_g.exchange(value);
+  if (opt == 2) return g_opt_simt.exchange(value);
+  return -1;
+}
+
+int64_t mcl_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// Shared device/host helpers for libmcl_sm100: PTX wrappers (mbarrier, TMA, tcgen05),
+// the order-preserving float key, and the partial-result ("slot") layout every scan
+// kernel writes and the merge kernel reads.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mcl {
+
+constexpr int kBlockM = 128;        // query rows per CTA tile  (UMMA M, TMEM lanes)
+constexpr int kBlockN = 256;        // table rows per tile      (UMMA N, TMEM columns)
+constexpr int kBlockK = 64;         // bf16 per K slice = 128 B = one SWIZZLE_128B row
+constexpr int kCandCap = 128;       // candidate-buffer entries per query row and slot
+constexpr int kChunk = 32;          // score columns one tcgen05.ld hands a thread
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---- order-preserving float <-> uint32 key (larger float <=> larger key) -----------
+__host__ __device__ __forceinline__ uint32_t f2key(float v) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(v);
+#else
+  union { float f; uint32_t u; } c; c.f = v; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key2f(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// ---- partial-result slots ------------------------------------------------------------
+// One slot = the partial answer of ONE CTA for ONE row block over a contiguous range of
+// table tiles: per row an unsorted candidate list (y value, local table row), its length,
+// and (m, s, sum_z, z_label) over that range.  Slots live in the caller's workspace.
+struct SlotView {
+  uint2* cand;   // [nslots][kBlockM][kCandCap]  (.x = float bits of y, .y = local row)
+  int* cnt;      // [nslots][kBlockM]
+  float4* stats; // [nslots][kBlockM]
+};
+
+// How the merge finds the slots of a row block (mirrors the scan kernels' schedules).
+struct SlotMap {
+  int mode;     // 0: stream-K groups (tcgen05 scan), 1: dense [row block][split] (SIMT scan)
+  int g;        // mode 0: row blocks per group
+  int jpg;      // mode 0: tile-jobs per group
+  int num_vt;   // mode 0: table tiles
+  int max_seg;  // mode 0: slots reserved per CTA
+  int nsplit;   // mode 1: V splits per row block
+};
+
+__host__ __device__ __forceinline__ int slotmap_count(const SlotMap& sm, int rb, int* first) {
+  if (sm.mode == 1) { *first = 0; return sm.nsplit; }
+  const int rg = rb / sm.g;
+  const long long j0 = (long long)rg * sm.num_vt, j1 = j0 + sm.num_vt - 1;
+  const int q0 = (int)(j0 / sm.jpg), q1 = (int)(j1 / sm.jpg);
+  *first = q0;
+  return q1 - q0 + 1;
+}
+__host__ __device__ __forceinline__ int slotmap_slot(const SlotMap& sm, int rb, int first, int i) {
+  if (sm.mode == 1) return rb * sm.nsplit + i;
+  const int rg = rb / sm.g, r = rb % sm.g;
+  const int q = first + i;
+  const int seg = rg - (int)(((long long)q * sm.jpg) / sm.num_vt);
+  return (q * sm.g + r) * sm.max_seg + seg;
+}
+
+#ifdef __CUDACC__
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// 2-D TMA tile load, completion on an mbarrier (bytes counted as a transaction).
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, uint32_t bar,
+                                            int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// tcgen05 -------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 in, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor for a K-major SWIZZLE_128B tile (rows of 128 B, 8-row
+// atoms 1024 B apart): start>>4 | LBO(unused)=1 | SBO=1024>>4 | version=1 | layout=SW128.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3, M>>4.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+#endif  // __CUDACC__
+
+}  // namespace mcl

@@ -1,0 +1,63 @@
+// Host-side launch interfaces shared by the translation units of libmcl_sm100.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace mcl {
+
+struct ScanArgs {
+  const void* q;
+  const void* table;
+  int dtype;                 // 0 bf16, 1 f32
+  int64_t Q, V, D, ldq, ldt;
+  const float* inv_q;        // nullable
+  const float* inv_t;        // nullable
+  float scale;
+  int k;
+  int64_t index_base;
+  const int64_t* labels;     // nullable
+  float* dbg_scores;         // nullable, [Q,V]
+};
+
+// Tile schedule of the tcgen05 scan (see scan_tc.cu): `grid` CTAs in groups of g; group q
+// owns tile-jobs [q*jpg, (q+1)*jpg) of the (row-group major, table-tile minor) job list.
+struct TcSchedule {
+  int num_rb, num_vt, num_kb;
+  int g, num_groups, num_rg, jpg, max_seg, grid;
+  long long total_jobs;
+};
+TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
+                            int force_g);
+
+struct Workspace {
+  SlotView sv;
+  int nslots;
+  size_t bytes;
+};
+// carve `nslots` slots out of a caller buffer (base may be null to only size it)
+Workspace carve_workspace(void* base, int nslots);
+
+cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
+                           cudaStream_t s, char* err, size_t errlen);
+cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, cudaStream_t s);
+
+// slots -> final [Q,k] / [Q,4]
+cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& sm, int64_t Q, int k,
+                               const float* inv_q, float scale, int64_t index_base,
+                               float* topk_val, int64_t* topk_idx, float* row_stats,
+                               cudaStream_t s);
+// R per-shard results (rank r's arrays start r * stride bytes after the base) -> final
+cudaError_t launch_merge_ranks(const float* val, const int64_t* idx, const float* stats,
+                               size_t val_stride, size_t idx_stride, size_t stats_stride, int R,
+                               int64_t Q, int k, float* out_val, int64_t* out_idx,
+                               float* out_stats, cudaStream_t s);
+
+cudaError_t launch_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                                float* out, cudaStream_t s);
+cudaError_t launch_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t ld,
+                               const int64_t* offsets, const int64_t* ids, int64_t Q,
+                               int normalize, void* out, int64_t ld_out, int* bad_flag,
+                               cudaStream_t s);
+
+}  // namespace mcl

@@ -1,0 +1,202 @@
+// Merge kernels: (1) the partial-result slots of one scan launch -> final [Q,k] / [Q,4];
+// (2) R dense per-shard results -> final (the step after the NCCL all-gather).
+// One warp per query row; a running sorted list of 64 (key) entries lives in registers,
+// two per lane, and is updated by warp-shuffle bitonic networks.  Keys are 64 bit:
+// high word = order-preserving float key, low word = ~row index, so a plain descending
+// sort realises "value desc, index asc" -- the documented lowest-index-wins tie rule.
+#include "kernels.h"
+
+namespace mcl {
+
+__device__ __forceinline__ uint64_t pack_key(float v, uint32_t idx) {
+  return ((uint64_t)f2key(v) << 32) | (uint64_t)(uint32_t)(~idx);
+}
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int j) {
+  return __shfl_xor_sync(0xffffffffu, v, j);
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+__device__ __forceinline__ uint64_t max64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// compare-exchange stage j (< 32) for element position p; desc = block sorted descending
+__device__ __forceinline__ uint64_t cx(uint64_t mine, int j, bool lower, bool desc) {
+  const uint64_t other = shfl_xor64(mine, j);
+  return (lower == desc) ? max64(mine, other) : min64(mine, other);
+}
+
+// Element p = i*32 + lane lives in register k[i] of `lane`.
+// Sorts all 64 descending starting from bitonic-network size `first_size`
+// (2 = full sort, 64 = bitonic merge of an already bitonic sequence).
+__device__ __forceinline__ void bitonic64_desc(uint64_t& k0, uint64_t& k1, int lane,
+                                               int first_size) {
+  for (int size = first_size; size <= 64; size <<= 1) {
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j == 32) {  // partner is the other register of this lane; size == 64: descending
+        const uint64_t hi = max64(k0, k1), lo = min64(k0, k1);
+        k0 = hi; k1 = lo;
+      } else {
+        const bool lower = (lane & j) == 0;
+        const bool desc0 = (size == 64) ? true : (size == 32 ? true : ((lane & size) == 0));
+        const bool desc1 = (size == 64) ? true : (size == 32 ? false : ((lane & size) == 0));
+        k0 = cx(k0, j, lower, desc0);
+        k1 = cx(k1, j, lower, desc1);
+      }
+    }
+  }
+}
+
+struct TopList {
+  uint64_t r0, r1;  // running top-64, descending over p = i*32 + lane
+  __device__ __forceinline__ void init() { r0 = 0ull; r1 = 0ull; }
+  // merge a batch of 64 unsorted keys (b0 = positions 0..31, b1 = 32..63)
+  __device__ __forceinline__ void push(uint64_t b0, uint64_t b1, int lane) {
+    bitonic64_desc(b0, b1, lane, 2);
+    // reversed batch: position p takes batch element 63 - p
+    const uint64_t rb0 = shfl64(b1, 31 - lane);
+    const uint64_t rb1 = shfl64(b0, 31 - lane);
+    r0 = max64(r0, rb0);
+    r1 = max64(r1, rb1);
+    bitonic64_desc(r0, r1, lane, 64);
+  }
+};
+
+__global__ void __launch_bounds__(128)
+merge_slots_kernel(SlotView sv, SlotMap sm, int Q, int k, const float* __restrict__ inv_q,
+                   float scale, long long index_base, float* __restrict__ topk_val,
+                   long long* __restrict__ topk_idx, float4* __restrict__ row_stats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= Q) return;
+  const int rb = row / kBlockM, r_in = row % kBlockM;
+  int first;
+  const int ns = slotmap_count(sm, rb, &first);
+
+  TopList top; top.init();
+  float m = -INFINITY;
+  // pass 1: stats max (lanes stride over slots)
+  for (int i = lane; i < ns; i += 32) {
+    const int slot = slotmap_slot(sm, rb, first, i);
+    m = fmaxf(m, sv.stats[(size_t)slot * kBlockM + r_in].x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f, sum_z = 0.f, z_label = 0.f;
+  for (int i = lane; i < ns; i += 32) {
+    const int slot = slotmap_slot(sm, rb, first, i);
+    const float4 st = sv.stats[(size_t)slot * kBlockM + r_in];
+    s += (st.y > 0.f) ? st.y * expf(st.x - m) : 0.f;
+    sum_z += st.z;
+    z_label += st.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sum_z += __shfl_xor_sync(0xffffffffu, sum_z, o);
+    z_label += __shfl_xor_sync(0xffffffffu, z_label, o);
+  }
+  if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
+
+  // pass 2: candidates, 64 at a time
+  for (int i = 0; i < ns; ++i) {
+    const int slot = slotmap_slot(sm, rb, first, i);
+    const int n = sv.cnt[(size_t)slot * kBlockM + r_in];
+    const uint2* b = sv.cand + ((size_t)slot * kBlockM + r_in) * kCandCap;
+    for (int base = 0; base < n; base += 64) {
+      uint64_t b0 = 0ull, b1 = 0ull;
+      const int j0 = base + lane, j1 = base + 32 + lane;
+      if (j0 < n) { const uint2 e = b[j0]; b0 = pack_key(__uint_as_float(e.x), e.y); }
+      if (j1 < n) { const uint2 e = b[j1]; b1 = pack_key(__uint_as_float(e.x), e.y); }
+      top.push(b0, b1, lane);
+    }
+  }
+  const float rs = (inv_q ? inv_q[row] : 1.f) * scale;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int p = i * 32 + lane;
+    const uint64_t key = i ? top.r1 : top.r0;
+    if (p < k) {
+      const bool empty = (key == 0ull);
+      topk_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32)) * rs;
+      topk_idx[(size_t)row * k + p] =
+          empty ? -1ll : index_base + (long long)(uint32_t)(~(uint32_t)key);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+merge_ranks_kernel(const char* __restrict__ val_b, const char* __restrict__ idx_b,
+                   const char* __restrict__ stats_b, size_t val_stride, size_t idx_stride,
+                   size_t stats_stride, int R, int Q, int k, float* __restrict__ out_val,
+                   long long* __restrict__ out_idx, float4* __restrict__ out_stats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= Q) return;
+  float m = -INFINITY;
+  auto stats_of = [&](int r) {
+    return reinterpret_cast<const float4*>(stats_b + (size_t)r * stats_stride)[row];
+  };
+  for (int r = lane; r < R; r += 32) m = fmaxf(m, stats_of(r).x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f, sum_z = 0.f, z_label = 0.f;
+  for (int r = lane; r < R; r += 32) {
+    const float4 st = stats_of(r);
+    s += (st.y > 0.f) ? st.y * expf(st.x - m) : 0.f;
+    sum_z += st.z;
+    z_label += st.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sum_z += __shfl_xor_sync(0xffffffffu, sum_z, o);
+    z_label += __shfl_xor_sync(0xffffffffu, z_label, o);
+  }
+  if (lane == 0) out_stats[row] = make_float4(m, s, sum_z, z_label);
+
+  TopList top; top.init();
+  for (int r = 0; r < R; ++r) {
+    const float* v = reinterpret_cast<const float*>(val_b + (size_t)r * val_stride) + (size_t)row * k;
+    const long long* ix =
+        reinterpret_cast<const long long*>(idx_b + (size_t)r * idx_stride) + (size_t)row * k;
+    uint64_t b0 = 0ull, b1 = 0ull;
+    if (lane < k && ix[lane] >= 0) b0 = pack_key(v[lane], (uint32_t)ix[lane]);
+    if (lane + 32 < k && ix[lane + 32] >= 0) b1 = pack_key(v[lane + 32], (uint32_t)ix[lane + 32]);
+    top.push(b0, b1, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int p = i * 32 + lane;
+    const uint64_t key = i ? top.r1 : top.r0;
+    if (p < k) {
+      const bool empty = (key == 0ull);
+      out_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32));
+      out_idx[(size_t)row * k + p] = empty ? -1ll : (long long)(uint32_t)(~(uint32_t)key);
+    }
+  }
+}
+
+cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& sm, int64_t Q, int k,
+                               const float* inv_q, float scale, int64_t index_base,
+                               float* topk_val, int64_t* topk_idx, float* row_stats,
+                               cudaStream_t s) {
+  if (Q == 0) return cudaSuccess;
+  merge_slots_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, s>>>(
+      sv, sm, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
+      (float4*)row_stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_ranks(const float* val, const int64_t* idx, const float* stats,
+                               size_t val_stride, size_t idx_stride, size_t stats_stride, int R,
+                               int64_t Q, int k, float* out_val, int64_t* out_idx,
+                               float* out_stats, cudaStream_t s) {
+  if (Q == 0) return cudaSuccess;
+  merge_ranks_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, s>>>(
+      (const char*)val, (const char*)idx, (const char*)stats, val_stride, idx_stride, stats_stride,
+      R, (int)Q, k, out_val, (long long*)out_idx, (float4*)out_stats);
+  return cudaGetLastError();
+}
+
+}  // namespace mcl

@@ -1,0 +1,183 @@
+// HBM-bound row kernels (part (c) of the path): inverse L2 row norms and the multi-token
+// gather-mean(-normalise).  One warp per row, 128-bit coalesced loads, fp32 arithmetic.
+// Algorithmic bytes: inv-norm reads rows*dim*elt and writes rows*4; gather-mean reads
+// nnz*D*elt (+ the CSR arrays) and writes Q*D*elt.
+#include <float.h>
+#include "kernels.h"
+
+namespace mcl {
+
+constexpr float kTinyNorm = 10.0f * FLT_EPSILON;  // sklearn: norms below this become 1
+
+template <typename T> struct Vec;  // 16-byte vector of T
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = __bfloat1622float2(h[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+  __device__ static __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  __device__ static __forceinline__ float ld1(const float* p) { return *p; }
+  __device__ static __forceinline__ void st1(float* p, float v) { *p = v; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_inv_norm_kernel(const T* __restrict__ x, long long rows, int dim, long long ld,
+                    float* __restrict__ out) {
+  constexpr int N = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* p = x + row * ld;
+  const int nvec = dim / N;
+  float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+  int v = lane;
+  for (; v + 96 < nvec; v += 128) {  // four independent 16-byte loads in flight per lane
+    float a[N], b[N], c[N], d[N];
+    Vec<T>::load(p + (size_t)v * N, a);
+    Vec<T>::load(p + (size_t)(v + 32) * N, b);
+    Vec<T>::load(p + (size_t)(v + 64) * N, c);
+    Vec<T>::load(p + (size_t)(v + 96) * N, d);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      ss0 = fmaf(a[i], a[i], ss0); ss1 = fmaf(b[i], b[i], ss1);
+      ss2 = fmaf(c[i], c[i], ss2); ss3 = fmaf(d[i], d[i], ss3);
+    }
+  }
+  for (; v < nvec; v += 32) {
+    float a[N];
+    Vec<T>::load(p + (size_t)v * N, a);
+#pragma unroll
+    for (int i = 0; i < N; ++i) ss0 = fmaf(a[i], a[i], ss0);
+  }
+  for (int e = nvec * N + lane; e < dim; e += 32) {
+    const float a = Vec<T>::ld1(p + e);
+    ss1 = fmaf(a, a, ss1);
+  }
+  const float ss = warp_sum((ss0 + ss1) + (ss2 + ss3));
+  if (lane == 0) {
+    const float n = sqrtf(ss);
+    out[row] = (n < kTinyNorm) ? 1.0f : 1.0f / n;
+  }
+}
+
+// out[i,:] = mean of the gathered rows (fp32 sum in id order, true division, one rounding);
+// with `normalize` the fp32 mean is scaled by 1/||mean|| (zero rows stay zero) first.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_mean_kernel(const T* __restrict__ table, long long V, int D, long long ld,
+                   const long long* __restrict__ offsets, const long long* __restrict__ ids,
+                   long long Q, int normalize, T* __restrict__ out, long long ld_out,
+                   int* __restrict__ bad_flag) {
+  constexpr int N = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= Q) return;
+  const long long b = offsets[row], e = offsets[row + 1];
+  const int n = (int)(e - b);
+  const float fn = (float)(n > 0 ? n : 1);
+  const int nvec = D / N;
+  T* o = out + row * ld_out;
+
+  float inv = 1.f;
+  for (int pass = normalize ? 0 : 1; pass < 2; ++pass) {
+    float ss = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      float acc[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] = 0.f;
+      for (long long j = b; j < e; ++j) {
+        long long id = ids[j];
+        if (id < 0 || id >= V) { if (bad_flag) *bad_flag = 1; id = id < 0 ? 0 : V - 1; }
+        float a[N];
+        Vec<T>::load(table + id * ld + (size_t)v * N, a);
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] += a[i];
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[i] = acc[i] / fn;
+      if (pass == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) ss = fmaf(acc[i], acc[i], ss);
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] *= inv;
+        Vec<T>::store(o + (size_t)v * N, acc);
+      }
+    }
+    for (int c = nvec * N + lane; c < D; c += 32) {  // ragged tail of D
+      float acc = 0.f;
+      for (long long j = b; j < e; ++j) {
+        long long id = ids[j];
+        if (id < 0 || id >= V) { if (bad_flag) *bad_flag = 1; id = id < 0 ? 0 : V - 1; }
+        acc += Vec<T>::ld1(table + id * ld + c);
+      }
+      acc = acc / fn;
+      if (pass == 0) ss = fmaf(acc, acc, ss); else Vec<T>::st1(o + c, acc * inv);
+    }
+    if (pass == 0) {
+      const float nrm = sqrtf(warp_sum(ss));
+      inv = (nrm < kTinyNorm) ? 1.0f : 1.0f / nrm;
+    }
+  }
+}
+
+cudaError_t launch_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                                float* out, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == 0)
+    row_inv_norm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, rows, (int)dim, ld, out);
+  else
+    row_inv_norm_kernel<float><<<grid, 256, 0, s>>>((const float*)x, rows, (int)dim, ld, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t ld,
+                               const int64_t* offsets, const int64_t* ids, int64_t Q,
+                               int normalize, void* out, int64_t ld_out, int* bad_flag,
+                               cudaStream_t s) {
+  if (Q == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((Q + 7) / 8);
+  if (dtype == 0)
+    gather_mean_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
+        (const __nv_bfloat16*)table, V, (int)D, ld, (const long long*)offsets,
+        (const long long*)ids, Q, normalize, (__nv_bfloat16*)out, ld_out, bad_flag);
+  else
+    gather_mean_kernel<float><<<grid, 256, 0, s>>>(
+        (const float*)table, V, (int)D, ld, (const long long*)offsets, (const long long*)ids, Q,
+        normalize, (float*)out, ld_out, bad_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace mcl

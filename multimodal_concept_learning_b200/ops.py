@@ -1,0 +1,298 @@
+"""Host-side operators over CUDA tensors: thin wrappers that allocate outputs/workspace with
+torch, pass raw pointers to libmcl_sm100.so on torch's current stream, and register the
+calls as torch custom ops (``torch.ops.mcl.*``) so they compose with the rest of a torch
+program.  PyTorch is plumbing here (device memory, streams); all arithmetic of the path is
+in the CUDA library.  CPU tensors are rejected -- there is no fallback."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import MCL_DTYPE_BF16, MCL_DTYPE_F32, MCL_MAX_K, check, load
+
+IGNORE_INDEX = -100
+
+
+def _dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return MCL_DTYPE_BF16
+    if t.dtype == torch.float32:
+        return MCL_DTYPE_F32
+    raise TypeError(f"libmcl_sm100 takes bfloat16 (tcgen05 path) or float32 (check path), got {t.dtype}")
+
+
+def _require_cuda(*ts: Optional[Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("libmcl_sm100 operators need CUDA tensors (no CPU fallback); "
+                               "move the tensor to the GPU first")
+        if dev is not None and t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+        dev = t.device
+    assert dev is not None
+    return dev
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    """Inner dim contiguous, 16-byte aligned base and pitch -- else a contiguous copy."""
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got {tuple(t.shape)}")
+    es = t.element_size()
+    ok = (t.stride(1) == 1 or t.shape[1] == 1) and t.stride(0) >= t.shape[1] \
+        and (t.stride(0) * es) % 16 == 0 and t.data_ptr() % 16 == 0
+    if ok:
+        return t
+    c = t.contiguous()
+    if (c.stride(0) * es) % 16 != 0:   # pad the pitch to 16 bytes
+        pad = (-c.shape[1]) % (16 // es)
+        buf = torch.zeros((c.shape[0], c.shape[1] + pad), dtype=c.dtype, device=c.device)
+        buf[:, :c.shape[1]] = c
+        return buf[:, :c.shape[1]]
+    return c
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------
+# custom ops
+# --------------------------------------------------------------------------------------
+
+@torch.library.custom_op("mcl::row_inv_norm", mutates_args=(), device_types="cuda")
+def _row_inv_norm_op(x: Tensor) -> Tensor:
+    x = _rowmajor(x)
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().mcl_row_inv_norm(x.data_ptr(), _dtype_code(x), x.shape[0], x.shape[1],
+                                      x.stride(0), out.data_ptr(), _stream(x.device)))
+    return out
+
+
+@_row_inv_norm_op.register_fake
+def _(x):
+    return x.new_empty(x.shape[0], dtype=torch.float32)
+
+
+@torch.library.custom_op("mcl::gather_mean", mutates_args=(), device_types="cuda")
+def _gather_mean_op(table: Tensor, offsets: Tensor, ids: Tensor, normalize: bool) -> Tensor:
+    table = _rowmajor(table)
+    Q = offsets.numel() - 1
+    D = table.shape[1]
+    es = table.element_size()
+    ld_out = D + ((-D) % (16 // es))
+    buf = torch.empty((Q, ld_out), dtype=table.dtype, device=table.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=table.device)
+    with torch.cuda.device(table.device):
+        check(load().mcl_gather_mean(table.data_ptr(), _dtype_code(table), table.shape[0], D,
+                                     table.stride(0), offsets.data_ptr(), ids.data_ptr(), Q,
+                                     int(normalize), buf.data_ptr(), ld_out, flag.data_ptr(),
+                                     _stream(table.device)))
+    out = buf[:, :D]
+    return out if ld_out == D else out.contiguous()
+
+
+@_gather_mean_op.register_fake
+def _(table, offsets, ids, normalize):
+    return table.new_empty((offsets.numel() - 1, table.shape[1]))
+
+
+@torch.library.custom_op("mcl::concept_scan", mutates_args=(), device_types="cuda")
+def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
+                     inv_norm_t: Optional[Tensor], labels: Optional[Tensor], scale: float,
+                     k: int, index_base: int) -> Tuple[Tensor, Tensor, Tensor]:
+    lib = load()
+    dev = q.device
+    Q, D = q.shape
+    V = table.shape[0]
+    code = _dtype_code(q)
+    val = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.mcl_concept_scan(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
+                                   table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t),
+                                   float(scale), k, index_base, _ptr(labels), val.data_ptr(),
+                                   idx.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes,
+                                   _stream(dev)))
+    return val, idx, stats
+
+
+@_concept_scan_op.register_fake
+def _(q, table, inv_norm_q, inv_norm_t, labels, scale, k, index_base):
+    Q = q.shape[0]
+    return (q.new_empty((Q, k), dtype=torch.float32), q.new_empty((Q, k), dtype=torch.int64),
+            q.new_empty((Q, 4), dtype=torch.float32))
+
+
+@torch.library.custom_op("mcl::merge", mutates_args=(), device_types="cuda")
+def _merge_op(val: Tensor, idx: Tensor, stats: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    R, Q, k = val.shape
+    dev = val.device
+    val, idx, stats = val.contiguous(), idx.contiguous(), stats.contiguous()
+    o_val = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    o_idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    o_stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(load().mcl_merge(val.data_ptr(), idx.data_ptr(), stats.data_ptr(), R, Q, k,
+                               o_val.data_ptr(), o_idx.data_ptr(), o_stats.data_ptr(), _stream(dev)))
+    return o_val, o_idx, o_stats
+
+
+@_merge_op.register_fake
+def _(val, idx, stats):
+    R, Q, k = val.shape
+    return (val.new_empty((Q, k)), idx.new_empty((Q, k)), stats.new_empty((Q, 4)))
+
+
+# --------------------------------------------------------------------------------------
+# public Python API
+# --------------------------------------------------------------------------------------
+
+def row_inv_norm(x: Tensor) -> Tensor:
+    """1/||row|| in fp32, zero rows -> 1 (sklearn ``normalize`` semantics)."""
+    _require_cuda(x)
+    _dtype_code(x)
+    return torch.ops.mcl.row_inv_norm(x)
+
+
+def gather_mean(table: Tensor, offsets: Tensor, ids: Tensor, normalize: bool = False) -> Tensor:
+    """CSR gather + mean (+ L2 normalise): multi-token concept embeddings."""
+    dev = _require_cuda(table)
+    _dtype_code(table)
+    offsets = offsets.to(device=dev, dtype=torch.int64).contiguous()
+    ids = ids.to(device=dev, dtype=torch.int64).contiguous()
+    if offsets.numel() < 1:
+        raise ValueError("offsets must have Q+1 entries")
+    return torch.ops.mcl.gather_mean(table, offsets, ids, bool(normalize))
+
+
+@dataclass
+class ScanOutput:
+    topk_val: Tensor            # [Q,k] fp32, descending
+    topk_idx: Tensor            # [Q,k] int64 global table rows (ties: lowest row first)
+    stats: Tensor               # [Q,4] fp32: m, s, sum_z, z_label
+    vocab: int                  # V the loss normalises label smoothing by
+    labels: Optional[Tensor] = None
+    label_smoothing: float = 0.0
+
+    @property
+    def lse(self) -> Tensor:
+        return self.stats[:, 0] + torch.log(self.stats[:, 1])
+
+    @property
+    def loss_rows(self) -> Tensor:
+        """Per-row CE, 0 on ignored rows: (1-e)(lse - z_y) + e(lse - sum_z/V)."""
+        if self.labels is None:
+            raise ValueError("scan was run without labels")
+        e = self.label_smoothing
+        lse = self.lse
+        rows = (1.0 - e) * (lse - self.stats[:, 3]) + e * (lse - self.stats[:, 2] / self.vocab)
+        return torch.where(self.labels != IGNORE_INDEX, rows, torch.zeros_like(rows))
+
+    @property
+    def loss(self) -> Tensor:
+        """Mean over rows whose label is not -100 (``F.cross_entropy`` 'mean')."""
+        n = (self.labels != IGNORE_INDEX).sum()
+        return self.loss_rows.sum() / n
+
+
+def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
+                 normalize_t: bool = True, scale: float = 1.0, labels: Optional[Tensor] = None,
+                 label_smoothing: float = 0.0, inv_norm_q: Optional[Tensor] = None,
+                 inv_norm_t: Optional[Tensor] = None, index_base: int = 0,
+                 vocab_total: Optional[int] = None) -> ScanOutput:
+    """Fused similarity scan of ``q [Q,D]`` against ``table [V,D]``: row-wise top-k and the
+    log-sum-exp / cross-entropy statistics, without materialising the [Q,V] scores.
+    ``normalize_*`` select cosine (True) vs raw dot product (False); a cached
+    ``inv_norm_t`` (from :func:`row_inv_norm`) avoids re-reading the table."""
+    dev = _require_cuda(q, table, labels, inv_norm_q, inv_norm_t)
+    if q.dtype != table.dtype:
+        raise TypeError(f"q ({q.dtype}) and table ({table.dtype}) must have the same dtype")
+    _dtype_code(q)
+    if q.dim() != 2 or table.dim() != 2 or q.shape[1] != table.shape[1]:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} table {tuple(table.shape)}")
+    if not 1 <= k <= min(MCL_MAX_K, table.shape[0]):
+        raise ValueError(f"k={k} must be in [1, min(V, {MCL_MAX_K})]")
+    if not scale > 0:
+        raise ValueError("scale must be > 0")
+    q, table = _rowmajor(q), _rowmajor(table)
+    if normalize_q and inv_norm_q is None:
+        inv_norm_q = torch.ops.mcl.row_inv_norm(q)
+    if normalize_t and inv_norm_t is None:
+        inv_norm_t = torch.ops.mcl.row_inv_norm(table)
+    if inv_norm_q is not None:
+        inv_norm_q = inv_norm_q.to(torch.float32).contiguous()
+    if inv_norm_t is not None:
+        inv_norm_t = inv_norm_t.to(torch.float32).contiguous()
+        if inv_norm_t.data_ptr() % 16:
+            inv_norm_t = inv_norm_t.clone()
+    if labels is not None:
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+        if labels.shape != (q.shape[0],):
+            raise ValueError(f"labels must have shape [{q.shape[0]}]")
+    val, idx, stats = torch.ops.mcl.concept_scan(q, table, inv_norm_q, inv_norm_t, labels,
+                                                 float(scale), int(k), int(index_base))
+    return ScanOutput(val, idx, stats, int(vocab_total or table.shape[0]), labels,
+                      float(label_smoothing))
+
+
+def concept_scan_debug(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv_norm_t=None,
+                       scale: float = 1.0, labels=None, index_base: int = 0):
+    """Test hook: the same kernels, additionally dumping the score matrix [Q,V]."""
+    lib = load()
+    dev = _require_cuda(q, table)
+    q, table = _rowmajor(q), _rowmajor(table)
+    Q, D = q.shape
+    V = table.shape[0]
+    code = _dtype_code(q)
+    val = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
+    scores = torch.full((Q, V), float("nan"), dtype=torch.float32, device=dev)
+    if labels is not None:
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.mcl_concept_scan_debug(q.data_ptr(), table.data_ptr(), code, Q, V, D,
+                                         q.stride(0), table.stride(0), _ptr(inv_norm_q),
+                                         _ptr(inv_norm_t), float(scale), k, index_base,
+                                         _ptr(labels), val.data_ptr(), idx.data_ptr(),
+                                         stats.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         scores.data_ptr(), _stream(dev)))
+    return ScanOutput(val, idx, stats, V, labels), scores
+
+
+def merge(val: Tensor, idx: Tensor, stats: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Merge [R,Q,k] / [R,Q,k] / [R,Q,4] per-shard results."""
+    _require_cuda(val, idx, stats)
+    return torch.ops.mcl.merge(val.float(), idx.to(torch.int64), stats.float())
+
+
+def set_option(opt: int, value: int) -> int:
+    return int(load().mcl_set_option(opt, value))
+
+
+def launch_count() -> int:
+    return int(load().mcl_launch_count())
+
+
+def device_info() -> Tuple[int, int, int]:
+    import ctypes as C
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    check(load().mcl_device_info(C.byref(sm), C.byref(ma), C.byref(mi)))
+    return sm.value, ma.value, mi.value
