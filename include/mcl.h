@@ -123,6 +123,18 @@ int mcl_concept_scan_debug(const void* q, const void* table, int dtype, int64_t 
                            size_t workspace_bytes, float* scores_out, mcl_stream_t stream);
 
 /*
+ * Dense similarity matrix scores_out[i,j] = z_ij (fp32, [Q,V] contiguous) for SMALL Q x V:
+ * the all-pairs cosine matrix the token analysis turns into distances.
+ * Replaces the O(n^2) Python loop of per-pair `cosine_similarity` calls,
+ *   src/multimodal/token_embedding_analysis.py:237-246 (n = 6..1000 concept tokens).
+ */
+size_t mcl_similarity_workspace_bytes(int64_t Q, int64_t V, int64_t D, int dtype);
+int mcl_similarity_matrix(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
+                          int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                          const float* inv_norm_t, float scale, float* scores_out, void* workspace,
+                          size_t workspace_bytes, mcl_stream_t stream);
+
+/*
  * Merge R partial results (one per vocabulary shard): candidates are re-ranked by
  * (value desc, index asc); m* = max m_r, s* = sum s_r exp(m_r - m*); sum_z and z_label add.
  * val/idx/stats are [R,Q,k] / [R,Q,k] / [R,Q,4]; idx < 0 marks an empty candidate.
@@ -162,6 +174,13 @@ int64_t mcl_set_option(int opt, int64_t value);
 
 /* number of kernel launches the library has enqueued in this process (for bench.py) */
 int64_t mcl_launch_count(void);
+
+/*
+ * Host-only introspection of the tcgen05 scan's tile schedule for a device with `sm_count`
+ * SMs: plan_out[10] = {row blocks, table tiles, K slices, group size g, groups, row groups,
+ * jobs per group, slots per CTA, grid, total jobs}.  Needs no GPU (used by the CPU tests).
+ */
+int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out);
 
 #ifdef __cplusplus
 }

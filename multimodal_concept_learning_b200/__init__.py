@@ -15,7 +15,8 @@ library and fails loudly if it has not been built (there is no CPU fallback).
 """
 from ._lib import MCL_MAX_K, MclError, LIB_PATH  # noqa: F401
 from .ops import (ScanOutput, concept_scan, concept_scan_debug, device_info, gather_mean,  # noqa: F401
+                  similarity_matrix,
                   launch_count, merge, row_inv_norm, set_option)
 
-__all__ = ["concept_scan", "concept_scan_debug", "row_inv_norm", "gather_mean", "merge",
+__all__ = ["concept_scan", "concept_scan_debug", "similarity_matrix", "row_inv_norm", "gather_mean", "merge",
            "ScanOutput", "MclError", "MCL_MAX_K", "set_option", "launch_count", "device_info"]

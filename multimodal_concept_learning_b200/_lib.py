@@ -40,6 +40,9 @@ SIGNATURES = {
     "mcl_concept_scan_debug": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
                                       _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr,
                                       _ptr]),
+    "mcl_similarity_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
+    "mcl_similarity_matrix": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32,
+                                     _ptr, _ptr, _sz, _ptr]),
     "mcl_merge": (_i32, [_ptr, _ptr, _ptr, _i32, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
     "mcl_comm_unique_id": (_i32, [_ptr]),
     "mcl_comm_init": (_i32, [_ptr, _i32, _i32, C.POINTER(_ptr)]),
@@ -50,6 +53,7 @@ SIGNATURES = {
                                         _sz, _ptr, _i32, _i32, _ptr]),
     "mcl_set_option": (_i64, [_i32, _i64]),
     "mcl_launch_count": (_i64, []),
+    "mcl_plan_scan": (_i32, [_i64, _i64, _i64, _i32, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -275,6 +275,26 @@ int mcl_concept_scan_debug(const void* q, const void* table, int dtype, int64_t 
                    scores_out, (cudaStream_t)stream);
 }
 
+int mcl_similarity_matrix(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
+                          int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                          const float* inv_norm_t, float scale, float* scores_out, void* workspace,
+                          size_t workspace_bytes, mcl_stream_t stream) {
+  // The same scan kernels with the score dump on; the k=1 outputs go to the workspace tail.
+  if (!scores_out && Q > 0) return fail(MCL_ERR_BAD_ARG, "null scores_out");
+  const size_t need = mcl_scan_workspace_bytes(Q, V, D, 1, dtype);
+  const size_t extra = ((size_t)(Q > 0 ? Q : 0) * 32 + 255) & ~(size_t)255;
+  if (!workspace || workspace_bytes < need + extra)
+    return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B", workspace_bytes, need + extra);
+  char* tail = (char*)workspace + need;
+  return scan_impl(q, table, dtype, Q, V, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, 1, 0, nullptr,
+                   (float*)(tail + (size_t)Q * 16), (int64_t*)(tail + (size_t)Q * 24), (float*)tail,
+                   workspace, need, scores_out, (cudaStream_t)stream);
+}
+
+size_t mcl_similarity_workspace_bytes(int64_t Q, int64_t V, int64_t D, int dtype) {
+  return mcl_scan_workspace_bytes(Q, V, D, 1, dtype) + (((size_t)(Q > 0 ? Q : 0) * 32 + 255) & ~(size_t)255);
+}
+
 int mcl_merge(const float* val, const int64_t* idx, const float* stats, int R, int64_t Q, int k,
               float* out_val, int64_t* out_idx, float* out_stats, mcl_stream_t stream) {
   if (R < 1 || Q < 0 || k < 1 || k > MCL_MAX_K) return fail(MCL_ERR_BAD_ARG, "bad R/Q/k");
@@ -374,5 +394,14 @@ int64_t mcl_set_option(int opt, int64_t value) {
 }
 
 int64_t mcl_launch_count(void) { return g_launches.load(); }
+
+int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out) {
+  if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || !plan_out) return fail(MCL_ERR_BAD_ARG, "bad plan args");
+  const TcSchedule s = make_tc_schedule(Q, V_local, D, sm_count, (int)g_opt_ctas.load(), (int)g_opt_g.load());
+  const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.num_groups, s.num_rg, s.jpg, s.max_seg,
+                         s.grid, (int32_t)s.total_jobs};
+  for (int i = 0; i < 10; ++i) plan_out[i] = v[i];
+  return MCL_OK;
+}
 
 }  // extern "C"

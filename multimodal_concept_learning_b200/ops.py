@@ -277,6 +277,43 @@ def concept_scan_debug(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv
     return ScanOutput(val, idx, stats, V, labels), scores
 
 
+@torch.library.custom_op("mcl::similarity_matrix", mutates_args=(), device_types="cuda")
+def _similarity_matrix_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
+                          inv_norm_t: Optional[Tensor], scale: float) -> Tensor:
+    lib = load()
+    dev = q.device
+    Q, D = q.shape
+    V = table.shape[0]
+    code = _dtype_code(q)
+    out = torch.empty((Q, V), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.mcl_similarity_workspace_bytes(Q, V, D, code)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.mcl_similarity_matrix(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
+                                        table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t),
+                                        float(scale), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        _stream(dev)))
+    return out
+
+
+@_similarity_matrix_op.register_fake
+def _(q, table, inv_norm_q, inv_norm_t, scale):
+    return q.new_empty((q.shape[0], table.shape[0]), dtype=torch.float32)
+
+
+def similarity_matrix(q: Tensor, table: Tensor, *, normalize: bool = True, scale: float = 1.0) -> Tensor:
+    """Dense [Q,V] fp32 similarity matrix for SMALL problems (the all-pairs cosine matrix of
+    the token analysis).  Large scans should use :func:`concept_scan`, which never stores it."""
+    _require_cuda(q, table)
+    if q.dtype != table.dtype:
+        raise TypeError("q and table must have the same dtype")
+    _dtype_code(q)
+    q, table = _rowmajor(q), _rowmajor(table)
+    inv_q = torch.ops.mcl.row_inv_norm(q) if normalize else None
+    inv_t = torch.ops.mcl.row_inv_norm(table) if normalize else None
+    return torch.ops.mcl.similarity_matrix(q, table, inv_q, inv_t, float(scale))
+
+
 def merge(val: Tensor, idx: Tensor, stats: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     """Merge [R,Q,k] / [R,Q,k] / [R,Q,4] per-shard results."""
     _require_cuda(val, idx, stats)

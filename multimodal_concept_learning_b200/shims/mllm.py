@@ -1,0 +1,73 @@
+"""Shim for the LM head + loss that ``MLLM.forward`` reaches through
+``self.language_model(..., labels=labels)`` (``src/multimodal/mllm.py:115-120`` ->
+``modeling_gemma3.py:649-664`` -> ``loss_utils.py:45-67``).
+
+The reference materialises ``[B,T,V]`` bf16 logits, upcasts them to fp32 and runs
+``F.cross_entropy``; here hidden states go straight into the fused scan: loss from the
+online log-sum-exp, predictions from the k=1 top-k, logits never stored.  The LM head is
+the input-embedding table (tied, ``modeling_gemma3.py:593``): raw dot product, no
+normalisation, scale 1."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ._common import compute_device, to_kernel_dtype
+
+IGNORE_INDEX = -100
+
+
+@dataclass
+class FusedCausalLMOutput:
+    """The fields of HF's ``CausalLMOutputWithPast`` the reference's loops read."""
+    loss: Optional[torch.Tensor]
+    predicted_ids: torch.Tensor          # argmax over the vocabulary, [B,T] (-1 where not computed)
+    logits: None = None                  # never materialised
+
+
+def shift_labels(labels: torch.Tensor, ignore_index: int = IGNORE_INDEX) -> torch.Tensor:
+    """loss_utils.py:57-59: pad one ignore on the right, drop the first -> token t predicts t+1."""
+    return F.pad(labels, (0, 1), value=ignore_index)[..., 1:].contiguous()
+
+
+def lm_head_loss_and_argmax(hidden_states: torch.Tensor, embedding_table: torch.Tensor,
+                            labels: Optional[torch.Tensor] = None, *, rows: str = "labelled",
+                            inv_norm_table=None) -> FusedCausalLMOutput:
+    """hidden [B,T,D] x table [V,D].  ``rows``: "all" scans every position (what HF computes);
+    "labelled" scans only positions that the loss (shifted mask) or the reference's accuracy
+    (unshifted mask, multimodal_training.py:282) reads -- identical loss and accuracy, ~100x
+    fewer query rows with the reference's answer-only supervision."""
+    dev = compute_device(hidden_states, embedding_table)
+    B, T, D = hidden_states.shape
+    h = to_kernel_dtype(hidden_states.detach()).to(dev).reshape(B * T, D)
+    table = to_kernel_dtype(embedding_table.detach()).to(dev)
+    if h.dtype != table.dtype:
+        h = h.to(table.dtype)
+    shifted = None
+    if labels is not None:
+        labels = labels.to(dev)
+        shifted = shift_labels(labels).reshape(-1)
+    if rows == "all" or labels is None:
+        sel = None
+        q, lab = h, shifted
+    else:
+        need = (shifted != IGNORE_INDEX) | (labels.reshape(-1) != IGNORE_INDEX)
+        sel = need.nonzero().flatten()
+        q, lab = h[sel], shifted[sel]
+    pred = torch.full((B * T,), -1, dtype=torch.int64, device=dev)
+    loss = None
+    if q.shape[0] > 0:
+        out = ops.concept_scan(q, table, 1, normalize_q=False, normalize_t=False, labels=lab)
+        if sel is None:
+            pred = out.topk_idx[:, 0]
+        else:
+            pred[sel] = out.topk_idx[:, 0]
+        if lab is not None:
+            loss = out.loss           # mean over rows with a shifted label (reduction='mean')
+    elif labels is not None:
+        loss = torch.tensor(float("nan"), device=dev)    # F.cross_entropy over zero valid rows
+    return FusedCausalLMOutput(loss=loss, predicted_ids=pred.reshape(B, T))

@@ -101,6 +101,8 @@ def gen_a1():
         with contextlib.redirect_stdout(io.StringIO()):
             r = tea.calculate_color_embedding_correlation(e, ood, reg, ood_ids, reg_ids, labels_mapping)
         out[f"r_{tag}"] = np.float64(r)
+    with open(os.path.join(OUT, name), "w") as f:   # the label map is part of the fixture
+        json.dump(labels_mapping, f, indent=1)
     np.savez(os.path.join(OUT, "a1_color_correlation.npz"),
              mapping_name=name, ood_ids=np.array(ood_ids), reg_ids=np.array(reg_ids),
              table_initial=emb["initial"].float().numpy(), table_epoch3=emb["epoch_3"].float().numpy(),

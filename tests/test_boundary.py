@@ -1,0 +1,131 @@
+"""CPU: the C-ABI boundary -- the library builds for sm_100a, loads, exports every symbol
+include/mcl.h declares, validates arguments before touching a device, and its tile
+schedule / slot map (host logic) covers every (row block, table tile) exactly once."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mcl.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcl_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib_built):
+    from multimodal_concept_learning_b200 import _lib
+    lib = C.CDLL(lib_built)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in mcl.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in _lib.py"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert _lib.load().mcl_version() == 100
+
+
+def test_library_is_sm100a_native(lib_built):
+    out = subprocess.run(["cuobjdump", "-lelf", lib_built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):      # tcgen05.mma, tcgen05.ld, TMA
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
+    assert "HMMA.16816" not in sass                       # no legacy mma.sync path
+
+
+def test_no_cpu_fallback(lib_built):
+    import multimodal_concept_learning_b200 as mcl
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mcl.concept_scan(torch.zeros(4, 8), torch.zeros(9, 8), 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mcl.row_inv_norm(torch.zeros(4, 8))
+    # the product package must not import the oracle
+    pkg = os.path.join(ROOT, "multimodal_concept_learning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_argument_validation_needs_no_device(lib_built):
+    from multimodal_concept_learning_b200 import _lib
+    lib = _lib.load()
+    buf = C.create_string_buffer(4096)
+    p = C.addressof(buf)
+    p16 = (p + 15) & ~15
+    common = dict(Q=4, V=9, D=8)
+    def scan(k=2, scale=1.0, dtype=0, q=p16, ldq=8):
+        return lib.mcl_concept_scan(q, p16, dtype, 4, 9, 8, ldq, 8, None, None, scale, k, 0, None,
+                                    p16, p16, p16, p16, 4096, None)
+    assert scan(k=0) == -1 and "k=0" in _lib.last_error()
+    assert scan(k=65) == -1
+    assert scan(k=10) == -1                  # k > V
+    assert scan(scale=0.0) == -1
+    assert scan(dtype=7) == -1
+    assert scan(ldq=4) == -1                 # ld < D
+    assert scan(q=p16 + 2) == -2             # misaligned base
+    assert scan(ldq=9, dtype=0) == -2        # pitch 18 B
+    rc = scan()                              # valid arguments: fails only for lack of a device
+    if not torch.cuda.is_available():
+        assert rc in (-5, -3), _lib.last_error()
+    with pytest.raises(_lib.MclError):
+        _lib.check(scan(k=0))
+    assert lib.mcl_scan_workspace_bytes(8192, 152064, 3584, 50, 0) > 0
+    assert lib.mcl_sharded_gather_bytes(100, 50, 8) >= 8 * (100 * 50 * 12 + 1600)
+
+
+def _plan(lib, Q, V, D, sm=148):
+    out = (C.c_int32 * 10)()
+    assert lib.mcl_plan_scan(Q, V, D, sm, out) == 0
+    keys = ["num_rb", "num_vt", "num_kb", "g", "num_groups", "num_rg", "jpg", "max_seg", "grid", "total_jobs"]
+    return dict(zip(keys, list(out)))
+
+
+@pytest.mark.parametrize("shape", [(16, 50257, 768), (4096, 49408, 768), (8192, 152064, 3584),
+                                   (65536, 128256, 4096), (32768, 1048576, 1024), (8192, 19008, 3584),
+                                   (1, 1, 8), (129, 257, 72), (700, 3000, 64)])
+@pytest.mark.parametrize("sm", [148, 5])
+def test_schedule_covers_every_tile_once(lib_built, shape, sm):
+    """Python restatement of the kernel's job walk and of merge.cu's slot map."""
+    from multimodal_concept_learning_b200 import _lib
+    lib = _lib.load()
+    Q, V, D = shape
+    p = _plan(lib, Q, V, D, sm)
+    assert p["num_rb"] == -(-Q // 128) and p["num_vt"] == -(-V // 256) and p["num_kb"] == -(-D // 64)
+    assert 1 <= p["grid"] <= sm and p["grid"] == p["num_groups"] * p["g"]
+    assert p["total_jobs"] == p["num_rg"] * p["num_vt"] and p["jpg"] * p["num_groups"] >= p["total_jobs"]
+    g, jpg, nvt, mseg = p["g"], p["jpg"], p["num_vt"], p["max_seg"]
+    if p["grid"] * p["max_seg"] > 5000 or p["total_jobs"] * g > 3_000_000:
+        pytest.skip("walk too long for a CPU test; arithmetic identical to smaller cases")
+    # kernel side: which (row block, tile) lands in which slot
+    written = {}
+    for cta in range(p["grid"]):
+        grp, member = divmod(cta, g)
+        j0, j1 = grp * jpg, min((grp + 1) * jpg, p["total_jobs"])
+        rg_first = j0 // nvt
+        for j in range(j0, j1):
+            rg, vt = divmod(j, nvt)
+            rb = rg * g + member
+            if rb < p["num_rb"]:
+                slot = cta * mseg + (rg - rg_first)
+                assert rg - rg_first < mseg
+                written.setdefault((rb, slot), []).append(vt)
+    # merge side: slots enumerated per row block
+    for rb in range(p["num_rb"]):
+        rg, r = divmod(rb, g)
+        q0, q1 = (rg * nvt) // jpg, (rg * nvt + nvt - 1) // jpg
+        tiles = []
+        for q in range(q0, q1 + 1):
+            slot = (q * g + r) * mseg + (rg - (q * jpg) // nvt)
+            assert (rb, slot) in written, (rb, slot)
+            tiles += written.pop((rb, slot))
+        assert sorted(tiles) == list(range(nvt)), f"row block {rb} tiles not covered exactly once"
+    assert not written, "kernel writes a slot the merge never reads"

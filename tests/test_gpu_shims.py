@@ -1,0 +1,138 @@
+"""GPU: the drop-in shims (reference function names) against the golden vectors produced by
+the reference's own functions, and against the oracle restatements."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import concept_scan_ref as R
+from oracle import reference_sites as S
+from oracle.gen_golden import ToyTokenizer
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gold(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    return lib_built
+
+
+def test_a1_color_correlation_shim_matches_reference_golden(capsys):
+    from multimodal_concept_learning_b200.shims.token_embedding_analysis import (
+        calculate_color_embedding_correlation, pairwise_cosine_similarity)
+    g = _gold("a1_color_correlation.npz")
+    mapping = json.load(open(os.path.join(GOLD, str(g["mapping_name"]))))
+    ood = [v for v in mapping.values() if v.startswith("<ood")]
+    reg = [v for v in mapping.values() if not v.startswith("<ood")]
+    t0 = torch.from_numpy(g["table_initial"]).to(torch.bfloat16)
+    t3 = torch.from_numpy(g["table_epoch3"]).to(torch.bfloat16)
+    emb = {"initial": t0, "epoch_0": t0.clone(), "epoch_3": t3}
+    ood_ids, reg_ids = g["ood_ids"].tolist(), g["reg_ids"].tolist()
+    r = calculate_color_embedding_correlation(emb, ood, reg, ood_ids, reg_ids, mapping)
+    assert isinstance(r, float) and abs(r - float(g["r_last"])) < 1e-5
+    assert "Pearson correlation coefficient" in capsys.readouterr().out      # same prints
+    r0 = calculate_color_embedding_correlation({"initial": t0}, ood, reg, ood_ids, reg_ids, mapping)
+    assert abs(r0 - float(g["r_initial_only"])) < 1e-5
+    # the matrix itself against sklearn, incl. a zero row and the duplicated OOD rows
+    from sklearn.metrics.pairwise import cosine_similarity
+    e = t0[ood_ids + reg_ids].clone()
+    e[1] = 0
+    cos = pairwise_cosine_similarity(e).cpu().numpy()
+    np.testing.assert_allclose(cos, cosine_similarity(e.float().numpy()), atol=2e-6)
+
+
+def test_a1_nearest_tokens_config1(capsys):
+    from multimodal_concept_learning_b200.shims.token_embedding_analysis import nearest_tokens
+    from tests.util import check_topk
+    g = torch.Generator().manual_seed(40)
+    table = torch.randn(50257, 768, generator=g).to(torch.bfloat16)
+    ids = torch.randperm(50257, generator=g)[:16].tolist()
+    val, idx = nearest_tokens(table.cuda(), ids, k=50)
+    ref = R.concept_scan_ref(table[ids], table, 50, keep_scores=True)
+    check_topk(val, idx, ref.scores, 50, rtol=1e-4, atol=1e-5)
+    assert idx[:, 0].cpu().tolist() == ids                    # each token is its own nearest neighbour
+
+
+def test_a3_average_embeddings_shim_matches_reference_golden():
+    from multimodal_concept_learning_b200.shims.token_embedding_analysis_imagenet import \
+        average_embeddings_for_tokens
+    from multimodal_concept_learning_b200.shims.multi_token import (get_averaged_embedding,
+                                                                     get_averaged_embeddings)
+    g = _gold("a3_average_embeddings.npz")
+    tok = ToyTokenizer(int(g["V"]))
+    names = [str(n) for n in g["names"]]
+    t_bf = torch.from_numpy(g["table_initial"]).to(torch.bfloat16)
+    t_f32 = torch.from_numpy(g["table_epoch0"])
+    res = average_embeddings_for_tokens(tok, {"initial": t_bf, "epoch_0": t_f32}, names)
+    assert res["initial"].dtype == torch.bfloat16 and not res["initial"].is_cuda     # same type/device out
+    assert torch.equal(res["initial"].float(), torch.from_numpy(g["out_initial"]))   # bit-exact
+    np.testing.assert_allclose(res["epoch_0"].numpy(), g["out_epoch0"], rtol=3e-7, atol=1e-7)
+    assert average_embeddings_for_tokens(tok, {}, names) == {}
+    assert average_embeddings_for_tokens(tok, {"initial": t_bf}, [])["initial"].shape == (0, t_bf.shape[1])
+    # notebook twin, CUDA-resident table
+    one = get_averaged_embedding(names[1], tok, t_bf.cuda())
+    assert torch.equal(one.cpu().float(), torch.from_numpy(g["out_initial"])[1])
+    many = get_averaged_embeddings([n for n in names if n], tok, t_f32.cuda(), normalize=True)
+    want = torch.from_numpy(g["out_epoch0"])[[i for i, n in enumerate(names) if n]]
+    want = want / want.norm(dim=1, keepdim=True)              # notebook cell 3 line 16
+    torch.testing.assert_close(many.cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+def test_a4_a5_lm_head_shim_matches_reference_golden():
+    from multimodal_concept_learning_b200.shims.mllm import lm_head_loss_and_argmax
+    from multimodal_concept_learning_b200.shims.multimodal_training import (count_yes_no_matches,
+                                                                             evaluate_hidden_batches)
+    g = _gold("a4_a5_mllm_head.npz")
+    hidden = torch.from_numpy(g["hidden"]).to(torch.bfloat16)
+    table = torch.from_numpy(g["table"]).to(torch.bfloat16)
+    labels = torch.from_numpy(g["labels"])
+    ref_logits = torch.from_numpy(g["logits"])                # the reference's bf16 logits
+    tok = ToyTokenizer(table.shape[0], int(g["yes_id"]), int(g["no_id"]))
+    for rows in ("labelled", "all"):
+        out = lm_head_loss_and_argmax(hidden.cuda(), table.cuda(), labels.cuda(), rows=rows)
+        # bf16 bound of north_star (the reference rounds its logits to bf16 before the CE)
+        assert abs(float(out.loss) - float(g["loss"])) <= 1e-2 * abs(float(g["loss"]))
+        # tighter: against the exact scores the kernel is meant to compute
+        exact, _ = S.causal_lm_head_loss_ref(hidden.double(), table.double(), labels, logits_dtype=torch.float64)
+        assert abs(float(out.loss) - float(exact)) <= 1e-4 * abs(float(exact))
+        pred = out.predicted_ids.cpu()
+        mask = labels != -100 if rows == "labelled" else torch.ones_like(labels, dtype=torch.bool)
+        ref_pred = ref_logits.argmax(-1)
+        differs = (pred != ref_pred) & mask
+        # where the fused argmax differs from the bf16-logit argmax it must be a bf16 near-tie
+        z = (hidden.double().reshape(-1, hidden.shape[-1]) @ table.double().T).reshape(ref_logits.shape)
+        for b, t in differs.nonzero().tolist():
+            assert z[b, t, pred[b, t]] >= z[b, t, ref_pred[b, t]] - 1e-12
+        c, n = count_yes_no_matches(pred, labels, tok)
+        assert n == 2
+    ev = evaluate_hidden_batches([{"hidden_states": hidden.cuda(), "labels": labels.cuda()}], table.cuda(), tok)
+    assert set(ev) == {"test_loss", "test_acc"}
+    assert abs(ev["test_loss"] - float(g["test_loss"])) <= 1e-2 * abs(float(g["test_loss"]))
+    exact_pred = z.argmax(-1)
+    c_exact, n_exact = S.evaluate_predictions_ref(z, labels, tok)[:2]
+    assert abs(ev["test_acc"] - 100.0 * c_exact / n_exact) < 1e-9
+
+
+def test_a7_vision_head_shim_matches_golden():
+    from multimodal_concept_learning_b200.shims.vision_training import classifier_loss_and_top1
+    g = _gold("a7_vision_head.npz")
+    feats, w = torch.from_numpy(g["feats"]), torch.from_numpy(g["weight"])
+    labels = torch.from_numpy(g["labels"])
+    for eps in (0.0, 0.1):
+        loss, pred = classifier_loss_and_top1(feats.cuda(), w.cuda(), None, labels.cuda(), eps)
+        assert abs(float(loss) - float(g[f"loss_{eps}"])) <= 1e-4 * float(g[f"loss_{eps}"])
+        assert torch.equal(pred.cpu(), torch.from_numpy(g["predicted"]))         # first max wins
+    # with a bias and fp16 features (the vision launch script uses fp16 autocast)
+    bias = torch.linspace(-1, 1, w.shape[0])
+    loss, pred = classifier_loss_and_top1(feats.half().cuda(), w.half().cuda(), bias.cuda(), labels.cuda(), 0.1)
+    want, wpred, _ = S.vision_ce_top1_ref(feats.half().float(), w.half().float(), bias, labels, 0.1)
+    assert abs(float(loss) - float(want)) <= 1e-4 * float(want)
+    assert torch.equal(pred.cpu(), wpred)
