@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-sweep", action="store_true", help="skip the secondary workloads (N=1 only)")
+    ap.add_argument("--profile", action="store_true",
+                    help="kernel-only run for ncu: no sweep, no e2e, no CPU baseline (not a bench value)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: W >= 3
@@ -291,9 +293,9 @@ def main():
     mcl.device_info()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    res = run_workload(args.workload, args.steps, args.warmup, world, rank, device, True, sampler)
+    res = run_workload(args.workload, args.steps, args.warmup, world, rank, device, not args.profile, sampler)
     out = dict(base)
-    out.update({"value": res["value"], "ms_per_step": res["ms_per_step"], "e2e": res["e2e"],
+    out.update({"value": res["value"], "ms_per_step": res["ms_per_step"], "e2e": res.get("e2e"),
                 "gpu_launches": res["gpu_launches"], "clocks": res["clocks"]})
     shard_flops = 2.0 * w["Q"] * w["V"] * w["D"] / world
     achieved = shard_flops / (res["ms_per_step"] * 1e-3) / 1e12
@@ -301,7 +303,7 @@ def main():
                        "frac": achieved / pk["bf16_tflops"], "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],
                        "peak_source": pk["source"] + " (burst cuBLAS bf16)", "traffic": None,
                        "kernel": "scan_tc_kernel (per GPU; step time includes the merge kernel)"}
-    if world == 1 and rank == 0:
+    if world == 1 and rank == 0 and not args.profile:
         torch.set_num_threads(os.cpu_count() or 1)
         n = cpu_sample_size(w)
         t = cpu_reference_step(w, n)

@@ -168,7 +168,8 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
 /*
  * Tuning knobs (host-side, process-global).  opt: 0 = CTAs per launch (0 = all SMs),
  * 1 = row-block group size g of the tile scheduler (0 = heuristic), 2 = route bf16 inputs
- * through the CUDA-core check kernel instead of tcgen05 (tests only).  Returns the old value.
+ * through the CUDA-core check kernel instead of tcgen05 (tests only), 3 = record per-CTA
+ * start/end globaltimer stamps in the first 16 KB of the workspace.  Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);
 
@@ -177,8 +178,8 @@ int64_t mcl_launch_count(void);
 
 /*
  * Host-only introspection of the tcgen05 scan's tile schedule for a device with `sm_count`
- * SMs: plan_out[10] = {row blocks, table tiles, K slices, group size g, groups, row groups,
- * jobs per group, slots per CTA, grid, total jobs}.  Needs no GPU (used by the CPU tests).
+ * SMs: plan_out[10] = {row blocks, table tiles, K slices, group size g, groups ng, rounds,
+ * tiles per chunk, slots, grid, 0}.  Needs no GPU (used by the CPU tests).
  */
 int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out);
 

@@ -16,7 +16,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0};
+std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -78,7 +78,7 @@ int scan_nslots(int64_t Q, int64_t V, int64_t D, int dtype, int sm, TcSchedule* 
   if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
     TcSchedule s = make_tc_schedule(Q, V, D, sm, (int)g_opt_ctas.load(), (int)g_opt_g.load());
     if (sch_out) *sch_out = s;
-    return s.grid * s.max_seg;
+    return s.num_rb * s.ng * 2;   // two column halves per (row block, chunk)
   }
   const int ns = simt_nsplit(Q, V, sm);
   if (nsplit_out) *nsplit_out = ns;
@@ -119,25 +119,29 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   TcSchedule sch{};
   int nsplit = 1;
   const int nslots = scan_nslots(Q, V, D, dtype, di.sm, &sch, &nsplit);
-  Workspace ws = carve_workspace(workspace, nslots);
+  const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
+  Workspace ws = carve_workspace(workspace, nslots, num_rb);
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
-  ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg};
-  SlotMap sm{};
+  ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
+             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared};
+  int merge_split = 1;
   cudaError_t e;
   if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
     char msg[256] = "";
+    e = cudaMemsetAsync(ws.tau_shared, 0, ws.tau_bytes, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "memset of the shared thresholds");
     e = launch_scan_tc(a, sch, ws.sv, stream, msg, sizeof(msg));
     if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);
-    sm.mode = 0; sm.g = sch.g; sm.jpg = sch.jpg; sm.num_vt = sch.num_vt; sm.max_seg = sch.max_seg;
+    merge_split = sch.ng * 2;
   } else {
     e = launch_scan_simt(a, ws.sv, nsplit, stream);
     if (e != cudaSuccess) return cuda_fail(e, "scan_simt launch");
-    sm.mode = 1; sm.nsplit = nsplit;
+    merge_split = nsplit;
   }
   g_launches++;
-  e = launch_merge_slots(ws.sv, sm, Q, k, inv_q, scale, index_base, topk_val, topk_idx, row_stats, stream);
+  e = launch_merge_slots(ws.sv, merge_split, Q, k, inv_q, scale, index_base, topk_val, topk_idx, row_stats, stream);
   if (e != cudaSuccess) return cuda_fail(e, "merge launch");
   g_launches++;
   return MCL_OK;
@@ -251,7 +255,7 @@ size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, in
   if (!dev_info(&di)) { cudaGetLastError(); di.sm = 148; }
   if (Q <= 0 || V_local <= 0 || D <= 0) return 256;
   const int nslots = scan_nslots(Q, V_local, D, dtype, di.sm, nullptr, nullptr);
-  return carve_workspace(nullptr, nslots).bytes;
+  return carve_workspace(nullptr, nslots, (int)((Q + kBlockM - 1) / kBlockM)).bytes;
 }
 
 int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
@@ -390,6 +394,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 0) return g_opt_ctas.exchange(value);
   if (opt == 1) return g_opt_g.exchange(value);
   if (opt == 2) return g_opt_simt.exchange(value);
+  if (opt == 3) return g_opt_timing.exchange(value);
   return -1;
 }
 
@@ -398,8 +403,8 @@ int64_t mcl_launch_count(void) { return g_launches.load(); }
 int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out) {
   if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || !plan_out) return fail(MCL_ERR_BAD_ARG, "bad plan args");
   const TcSchedule s = make_tc_schedule(Q, V_local, D, sm_count, (int)g_opt_ctas.load(), (int)g_opt_g.load());
-  const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.num_groups, s.num_rg, s.jpg, s.max_seg,
-                         s.grid, (int32_t)s.total_jobs};
+  const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.ng, s.rounds, s.tpc, s.num_rb * s.ng * 2,
+                         s.grid, 0};
   for (int i = 0; i < 10; ++i) plan_out[i] = v[i];
   return MCL_OK;
 }

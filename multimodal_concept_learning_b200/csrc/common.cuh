@@ -43,32 +43,8 @@ struct SlotView {
   float4* stats; // [nslots][kBlockM]
 };
 
-// How the merge finds the slots of a row block (mirrors the scan kernels' schedules).
-struct SlotMap {
-  int mode;     // 0: stream-K groups (tcgen05 scan), 1: dense [row block][split] (SIMT scan)
-  int g;        // mode 0: row blocks per group
-  int jpg;      // mode 0: tile-jobs per group
-  int num_vt;   // mode 0: table tiles
-  int max_seg;  // mode 0: slots reserved per CTA
-  int nsplit;   // mode 1: V splits per row block
-};
-
-__host__ __device__ __forceinline__ int slotmap_count(const SlotMap& sm, int rb, int* first) {
-  if (sm.mode == 1) { *first = 0; return sm.nsplit; }
-  const int rg = rb / sm.g;
-  const long long j0 = (long long)rg * sm.num_vt, j1 = j0 + sm.num_vt - 1;
-  const int q0 = (int)(j0 / sm.jpg), q1 = (int)(j1 / sm.jpg);
-  *first = q0;
-  return q1 - q0 + 1;
-}
-__host__ __device__ __forceinline__ int slotmap_slot(const SlotMap& sm, int rb, int first, int i) {
-  if (sm.mode == 1) return rb * sm.nsplit + i;
-  const int rg = rb / sm.g, r = rb % sm.g;
-  const int q = first + i;
-  const int seg = rg - (int)(((long long)q * sm.jpg) / sm.num_vt);
-  return (q * sm.g + r) * sm.max_seg + seg;
-}
-
+// Slots of row block rb are rb*nsplit .. rb*nsplit + nsplit-1 (one per table chunk) for both
+// scan engines.
 #ifdef __CUDACC__
 // ---- PTX wrappers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -168,6 +144,35 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
         "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
+      : "memory");
+}
+
+// Split form for software pipelining: issue the load, wait later.  The wait names the
+// destination registers as in/out operands so the compiler cannot move a use above it.
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+        "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+        "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+        "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+        "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
       : "memory");
 }
 

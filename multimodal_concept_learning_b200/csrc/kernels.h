@@ -18,32 +18,36 @@ struct ScanArgs {
   int64_t index_base;
   const int64_t* labels;     // nullable
   float* dbg_scores;         // nullable, [Q,V]
+  void* timing;              // nullable, [grid][2] uint64 (tcgen05 scan only)
+  void* tau_shared;          // nullable, [num_rb*128] uint32 zeroed before launch (tcgen05 scan)
 };
 
-// Tile schedule of the tcgen05 scan (see scan_tc.cu): `grid` CTAs in groups of g; group q
-// owns tile-jobs [q*jpg, (q+1)*jpg) of the (row-group major, table-tile minor) job list.
+// Tile schedule of the tcgen05 scan (see scan_tc.cu): ng groups of g CTAs; in round r member m
+// owns row block r*g + m and group q scans table tiles [q*tpc, (q+1)*tpc); slot = rb*ng + q.
 struct TcSchedule {
   int num_rb, num_vt, num_kb;
-  int g, num_groups, num_rg, jpg, max_seg, grid;
-  long long total_jobs;
+  int g, ng, rounds, tpc, grid;
 };
 TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
                             int force_g);
 
 struct Workspace {
+  void* timing;   // [1024][2] uint64 at offset 0: per-CTA globaltimer start/end (debug option 3)
+  void* tau_shared;   // one threshold word per (padded) query row, shared between CTAs
+  size_t tau_bytes;
   SlotView sv;
   int nslots;
   size_t bytes;
 };
 // carve `nslots` slots out of a caller buffer (base may be null to only size it)
-Workspace carve_workspace(void* base, int nslots);
+Workspace carve_workspace(void* base, int nslots, int num_rb);
 
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen);
 cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, cudaStream_t s);
 
 // slots -> final [Q,k] / [Q,4]
-cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& sm, int64_t Q, int k,
+cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
                                const float* inv_q, float scale, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s);

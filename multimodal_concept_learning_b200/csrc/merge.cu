@@ -62,55 +62,91 @@ struct TopList {
   }
 };
 
-__global__ void __launch_bounds__(128)
-merge_slots_kernel(SlotView sv, SlotMap sm, int Q, int k, const float* __restrict__ inv_q,
+// One CTA (4 warps) per query row.  Warp w folds slots w, w+4, ... into its own running
+// top-64; candidates that cannot beat the warp's current k-th key are dropped before any
+// sorting (after the first slot almost all are), survivors are batched 64 at a time through
+// a small shared-memory queue.  Warp 0 then folds the other warps' lists and writes the row.
+constexpr int kMergeWarps = 4;
+constexpr int kPendCap = 96;
+
+__global__ void __launch_bounds__(32 * kMergeWarps)
+merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restrict__ inv_q,
                    float scale, long long index_base, float* __restrict__ topk_val,
                    long long* __restrict__ topk_idx, float4* __restrict__ row_stats) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= Q) return;
+  __shared__ unsigned long long pend[kMergeWarps][kPendCap];
+  __shared__ unsigned long long lists[kMergeWarps][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x;
   const int rb = row / kBlockM, r_in = row % kBlockM;
-  int first;
-  const int ns = slotmap_count(sm, rb, &first);
+  const int slot0 = rb * nsplit;
+  const unsigned lt = (1u << lane) - 1u;
+
+  if (warp == 0) {   // (m, s, sum_z, z_label) over the slots
+    float m = -INFINITY;
+    for (int i = lane; i < nsplit; i += 32)
+      m = fmaxf(m, sv.stats[(size_t)(slot0 + i) * kBlockM + r_in].x);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f, sum_z = 0.f, z_label = 0.f;
+    for (int i = lane; i < nsplit; i += 32) {
+      const float4 st = sv.stats[(size_t)(slot0 + i) * kBlockM + r_in];
+      s += (st.y > 0.f) ? st.y * expf(st.x - m) : 0.f;
+      sum_z += st.z;
+      z_label += st.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      sum_z += __shfl_xor_sync(0xffffffffu, sum_z, o);
+      z_label += __shfl_xor_sync(0xffffffffu, z_label, o);
+    }
+    if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
+  }
 
   TopList top; top.init();
-  float m = -INFINITY;
-  // pass 1: stats max (lanes stride over slots)
-  for (int i = lane; i < ns; i += 32) {
-    const int slot = slotmap_slot(sm, rb, first, i);
-    m = fmaxf(m, sv.stats[(size_t)slot * kBlockM + r_in].x);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float s = 0.f, sum_z = 0.f, z_label = 0.f;
-  for (int i = lane; i < ns; i += 32) {
-    const int slot = slotmap_slot(sm, rb, first, i);
-    const float4 st = sv.stats[(size_t)slot * kBlockM + r_in];
-    s += (st.y > 0.f) ? st.y * expf(st.x - m) : 0.f;
-    sum_z += st.z;
-    z_label += st.w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    sum_z += __shfl_xor_sync(0xffffffffu, sum_z, o);
-    z_label += __shfl_xor_sync(0xffffffffu, z_label, o);
-  }
-  if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
-
-  // pass 2: candidates, 64 at a time
-  for (int i = 0; i < ns; ++i) {
-    const int slot = slotmap_slot(sm, rb, first, i);
+  unsigned long long kth = 0ull;          // key of the warp's current k-th best (0 = none yet)
+  int npend = 0;
+  unsigned long long* q = pend[warp];
+  auto flush64 = [&]() {                  // fold the first 64 queued keys, keep the rest
+    const unsigned long long b0 = q[lane], b1 = q[32 + lane];
+    const unsigned long long rest = (64 + lane < npend) ? q[64 + lane] : 0ull;
+    __syncwarp();
+    top.push(b0, b1, lane);
+    npend -= 64;
+    if (lane < npend) q[lane] = rest;
+    __syncwarp();
+    const int p = k - 1;
+    kth = shfl64(p < 32 ? top.r0 : top.r1, p & 31);
+  };
+  for (int i = warp; i < nsplit; i += kMergeWarps) {
+    const int slot = slot0 + i;
     const int n = sv.cnt[(size_t)slot * kBlockM + r_in];
     const uint2* b = sv.cand + ((size_t)slot * kBlockM + r_in) * kCandCap;
-    for (int base = 0; base < n; base += 64) {
-      uint64_t b0 = 0ull, b1 = 0ull;
-      const int j0 = base + lane, j1 = base + 32 + lane;
-      if (j0 < n) { const uint2 e = b[j0]; b0 = pack_key(__uint_as_float(e.x), e.y); }
-      if (j1 < n) { const uint2 e = b[j1]; b1 = pack_key(__uint_as_float(e.x), e.y); }
-      top.push(b0, b1, lane);
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane;
+      unsigned long long key = 0ull;
+      if (j < n) { const uint2 e = b[j]; key = pack_key(__uint_as_float(e.x), e.y); }
+      const bool keep = key > kth;        // keys are unique, so > loses nothing
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) q[npend + __popc(km & lt)] = key;
+      npend += __popc(km);
+      __syncwarp();
+      if (npend >= 64) flush64();
     }
   }
+  if (npend > 0) {                        // tail: pad the queue to 64 with empty keys
+    if (lane + npend < 64) q[npend + lane] = 0ull;
+    if (lane + npend + 32 < 64) q[npend + 32 + lane] = 0ull;
+    __syncwarp();
+    npend = 64;
+    flush64();
+  }
+  lists[warp][lane] = top.r0;
+  lists[warp][32 + lane] = top.r1;
+  __syncthreads();
+  if (warp != 0) return;
+  for (int w = 1; w < kMergeWarps; ++w) top.push(lists[w][lane], lists[w][32 + lane], lane);
+
   const float rs = (inv_q ? inv_q[row] : 1.f) * scale;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -177,13 +213,13 @@ merge_ranks_kernel(const char* __restrict__ val_b, const char* __restrict__ idx_
   }
 }
 
-cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& sm, int64_t Q, int k,
+cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
                                const float* inv_q, float scale, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s) {
   if (Q == 0) return cudaSuccess;
-  merge_slots_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, s>>>(
-      sv, sm, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
+  merge_slots_kernel<<<(unsigned)Q, 32 * kMergeWarps, 0, s>>>(
+      sv, nsplit, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
       (float4*)row_stats);
   return cudaGetLastError();
 }

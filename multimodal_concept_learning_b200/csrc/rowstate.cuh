@@ -8,21 +8,39 @@
 // exp2 argument (a = rs * log2 e) and into the final outputs only.
 //
 // Top-k: a candidate is appended to the row's buffer (global memory, L2 resident) when
-// y > tau, tau being the k-th best value at the last compaction.  When fewer than 32 free
-// entries remain the WARP compacts that row cooperatively: exact k-th value by radix
-// select on order-preserving keys, stable keep of everything above it plus the earliest
-// ties.  Because table rows are visited in increasing order inside a slot, "earliest"
-// is "lowest index", which is the documented tie rule.
+// y > tau.  tau is a LOWER BOUND of the row's final k-th best score, from two sources:
+//   - the row's own buffer: when fewer than 32 free entries remain the WARP compacts it
+//     cooperatively -- a threshold with k..k+kSlack entries at or above it is found by
+//     bisection on the order-preserving keys (warp-wide counts), everything below is dropped;
+//   - the other CTAs scanning the same query row over other table chunks, which publish
+//     their thresholds through one word per row in global memory (atomicMax); any chunk's
+//     k-th best is a lower bound of the global k-th best.
+// Neither source can drop a member of the true top-k: an element is discarded only when k
+// others with a larger value -- or an equal value and a lower table row, because a chunk is
+// visited in increasing row order -- are known to exist.  The exact ordering, including the
+// lowest-index-wins tie rule, is established by merge.cu.  When bisection cannot separate
+// the entries (many exactly equal scores, e.g. duplicated table rows) the compaction falls
+// back to an exact radix select that keeps the earliest ties.
 #pragma once
 #include "common.cuh"
 
 namespace mcl {
 
+constexpr int kSlack = 14;   // a compaction leaves k .. k+kSlack entries
+
+// 2^x on the SFU (MUFU.EX2), one instruction: ~2 ulp, flushes results below 2^-126 to 0,
+// which is far inside the rtol of a sum of >= 1 terms of magnitude 1 (the row max).
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct RowState {
   float m;        // running max of y
   float s;        // sum exp2((y - m) * a)
   float sum_y;    // sum of y
-  float tau;      // append threshold
+  float tau;      // append threshold (strict: append when y > tau)
   float y_label;  // y at the label column (0 if not seen)
   int cnt;        // entries in the candidate buffer
   uint2* buf;     // this row's candidate buffer inside the active slot
@@ -56,12 +74,12 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
 
   // online log-sum-exp in base 2
   const float m_new = fmaxf(st.m, cm);
-  const float corr = exp2f((st.m - m_new) * a);  // first chunk: exp2(-inf) = 0, s is 0 anyway
+  const float corr = ex2_fast((st.m - m_new) * a);  // first chunk: exp2(-inf) = 0, s is 0 anyway
   const float mb = m_new * a;
   float acc = 0.f, sy = 0.f;
 #pragma unroll
   for (int i = 0; i < kChunk; ++i) {
-    acc += exp2f(fmaf(y[i], a, -mb));            // masked columns: exp2(-inf) = 0
+    acc += ex2_fast(fmaf(y[i], a, -mb));            // masked columns: exp2(-inf) = 0
     if (TAIL) sy += (i < n_valid) ? y[i] : 0.f; else sy += y[i];
   }
   st.s = fmaf(st.s, corr, acc);
@@ -80,19 +98,30 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
   }
 }
 
+__device__ __forceinline__ int warp_count_ge(const uint32_t (&key)[kCandCap / 32], uint32_t x) {
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < kCandCap / 32; ++i) c += (key[i] >= x) ? 1 : 0;
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
 // Warp-cooperative compaction of every row of this warp whose buffer could overflow on
 // the next chunk.  warp_buf = buffer of the warp's lane-0 row; rows are kCandCap apart.
-// Must be called by all 32 lanes (converged).
-__device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* warp_buf, int lane) {
+// tau_pub = this lane's word of the shared threshold array (nullable).  Must be called by
+// all 32 lanes (converged).
+__device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* warp_buf, int lane,
+                                                  uint32_t* tau_pub) {
   unsigned need = __ballot_sync(0xffffffffu, st.cnt + kChunk > kCandCap);
+  if (need == 0) return;
   const unsigned lt = (1u << lane) - 1u;
+  __threadfence_block();
+  __syncwarp();  // the owners' appends are visible to the warp
   while (need) {
     const int r = __ffs(need) - 1;
     need &= need - 1;
     const int n = __shfl_sync(0xffffffffu, st.cnt, r);
+    const uint32_t tau_key = f2key(__shfl_sync(0xffffffffu, st.tau, r));
     uint2* b = warp_buf + (size_t)r * kCandCap;
-    __threadfence_block();
-    __syncwarp();  // lane r's appends are visible to the warp
     uint32_t key[kCandCap / 32], idx[kCandCap / 32];
 #pragma unroll
     for (int i = 0; i < kCandCap / 32; ++i) {
@@ -104,24 +133,51 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
         idx[i] = e.y;
       }
     }
-    // radix select: key of the k-th largest entry; kr = how many of its ties to keep
-    uint32_t prefix = 0u;
-    int kr = k;
-#pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t want = (prefix >> bit) | 1u;
-      int c = 0;
+    // ---- bisection: x with k <= #{key >= x} <= k + kSlack ------------------------------
+    uint32_t mx = key[0];
 #pragma unroll
-      for (int i = 0; i < kCandCap / 32; ++i) c += ((key[i] >> bit) == want) ? 1 : 0;
-      const int tot = __reduce_add_sync(0xffffffffu, c);
-      if (tot >= kr) prefix |= (1u << bit); else kr -= tot;
+    for (int i = 1; i < kCandCap / 32; ++i) mx = max(mx, key[i]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    uint32_t lo = tau_key + 1u;                        // entries strictly above the threshold
+    uint32_t hi = (mx == 0xffffffffu) ? mx : mx + 1u;  // #{key >= hi} = 0 < k
+    uint32_t x = lo;
+    int cx = warp_count_ge(key, lo);
+    // (a threshold raised by another CTA can leave fewer than k live entries: keep just those)
+    bool found = (cx <= k + kSlack);
+#pragma unroll 1
+    for (int it = 0; it < 34 && !found && hi - lo > 1u; ++it) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      const int c = warp_count_ge(key, mid);
+      if (c < k) hi = mid;
+      else if (c > k + kSlack) lo = mid;
+      else { x = mid; cx = c; found = true; }
     }
+    uint32_t cls_lo, cls_hi;
+    int kr;
+    if (found) {                     // keep everything at or above x
+      cls_lo = x; cls_hi = 0xffffffffu; kr = cx;
+    } else {
+      // ---- exact radix select (ties): key of the k-th largest, kr = ties of it to keep ---
+      uint32_t prefix = 0u;
+      kr = k;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t want = (prefix >> bit) | 1u;
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < kCandCap / 32; ++i) c += ((key[i] >> bit) == want) ? 1 : 0;
+        const int tot = __reduce_add_sync(0xffffffffu, c);
+        if (tot >= kr) prefix |= (1u << bit); else kr -= tot;
+      }
+      cls_lo = prefix; cls_hi = prefix;
+    }
+    // entries above the class are kept; inside the class the first kr in buffer order
     __syncwarp();  // every lane holds its entries in registers before any overwrite
     int base = 0, ties_seen = 0;
 #pragma unroll
     for (int i = 0; i < kCandCap / 32; ++i) {
-      const bool gt = key[i] > prefix;
-      const bool eq = key[i] == prefix;
+      const bool gt = key[i] > cls_hi;
+      const bool eq = key[i] >= cls_lo && key[i] <= cls_hi;
       const unsigned eqm = __ballot_sync(0xffffffffu, eq);
       const bool keep = gt || (eq && (ties_seen + __popc(eqm & lt)) < kr);
       ties_seen += __popc(eqm);
@@ -129,9 +185,21 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
       if (keep) b[base + __popc(km & lt)] = make_uint2(__float_as_uint(key2f(key[i])), idx[i]);
       base += __popc(km);
     }
-    __syncwarp();
-    if (lane == r) { st.cnt = base; st.tau = key2f(prefix); }
+    if (lane == r) {
+      st.cnt = base;
+      if (base >= k) {                           // k entries at or above cls_lo are known
+        st.tau = fmaxf(st.tau, key2f(cls_lo));
+        if (tau_pub) atomicMax(tau_pub, cls_lo); // a lower bound of this row's final k-th best
+      }
+    }
   }
+  __syncwarp();
+}
+
+// Fold in the threshold other CTAs published for this row: keep y >= shared, i.e. y > the
+// float just below it (an equal score in another chunk may still lose the index tie-break).
+__device__ __forceinline__ void row_apply_shared_tau(RowState& st, uint32_t shared_key) {
+  if (shared_key > 1u) st.tau = fmaxf(st.tau, key2f(shared_key - 1u));
 }
 
 // Close a slot: candidate count and (m, s, sum_z, z_label) in z space for this row.

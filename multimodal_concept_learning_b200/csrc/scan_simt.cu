@@ -101,7 +101,7 @@ scan_simt_kernel(const T* __restrict__ q, const T* __restrict__ table, int Q, in
     if (n_valid == kChunk) row_process_chunk<false>(st, acc, col0, kChunk, a, lab_local);
     else row_process_chunk<true>(st, acc, col0, n_valid, a, lab_local);
     __syncwarp();
-    warp_compact_rows(st, k, warp_buf, lane);
+    warp_compact_rows(st, k, warp_buf, lane, nullptr);
   }
   row_flush(st, rs, sv.cnt + (size_t)slot * kBlockM + tid, sv.stats + (size_t)slot * kBlockM + tid);
 }

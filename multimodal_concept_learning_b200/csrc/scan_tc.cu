@@ -8,16 +8,19 @@
 //     online log-sum-exp, running sum, label pick-up and top-k filter are thread-private
 //     (rowstate.cuh) and the [Q x V] score matrix never leaves the SM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue.  A warp may only read the TMEM lane quarter warp_id % 4, so two warps
+// share each quarter and split the tile's 256 columns in halves (own row state, own slot):
+// two resident warps per scheduler hide each other's latencies.
 //
-// Scheduling: persistent CTAs.  The job list is (row-group, table tile) with a row-group =
-// g consecutive 128-query row blocks; CTA c belongs to group c / g as member c % g, and a
-// group owns a contiguous range of jobs ("stream-K" over the list), in which member r scans
-// row block rg*g + r.  The g members of a group walk the same table tiles at the same time,
-// so a table tile is fetched from HBM once per group and hit in L2 by the other members,
-// while the contiguous split keeps all 148 SMs busy for any Q.  Every (CTA, row block)
-// range ends in a partial-result slot; merge.cu combines the slots.
+// Scheduling: persistent CTAs in ng groups of g.  Work proceeds in rounds; in round r member m
+// of every group owns query row block r*g + m, and group q scans the q-th contiguous chunk of
+// table tiles ([q*tpc, (q+1)*tpc)).  So at any time the whole chip works on only g row blocks
+// (their query tiles stay L2 resident) and streams ng table chunks, each tile of which is
+// fetched from HBM once and hit in L2 by the other g-1 members of its group -- measured on
+// B200 this matters more than the last few percent of SM occupancy, because L2/HBM traffic
+// costs power and the kernel runs at the 1 kW cap.  Every (row block, chunk) pair ends in a
+// partial-result slot rb*ng + q; merge.cu combines the ng slots of a row block.
 #include <cuda.h>
 #include <stdio.h>
 #include <algorithm>
@@ -27,19 +30,20 @@
 namespace mcl {
 
 constexpr int kStages = 4;
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter: column halves
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr uint32_t kBBytes = kBlockN * kBlockK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;   // 48 KB
 constexpr uint32_t kTmemCols = 512;                   // 2 accumulator stages x 256 columns
 constexpr uint32_t kBarBytes = 256;
-constexpr uint32_t kTcSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+constexpr uint32_t kCsBytes = kEpiWarps * 2 * (kBlockN / 2) * 4;  // per epilogue warp: 2 x 128 table-row scales
+constexpr uint32_t kTcSmemBytes = kStages * kStageBytes + kBarBytes + kCsBytes + 1024;  // + align slack
 
 struct TcParams {
   int Q, V, D, k;
   int num_rb, num_vt, num_kb;
-  int g, jpg, max_seg;
-  long long total_jobs;
+  int g, ng, rounds, tpc;
   const float* inv_q;
   const float* inv_t;
   float scale;
@@ -47,6 +51,8 @@ struct TcParams {
   const long long* labels;
   SlotView sv;
   float* dbg_scores;
+  unsigned long long* timing;   // nullable: [grid][2] globaltimer at CTA start / end
+  uint32_t* tau_shared;         // [num_rb*128] order-preserving keys, zeroed before the launch
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -65,6 +71,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8u * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long t_start = 0;
+  if (p.timing && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -73,7 +81,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (warp == 1) {
     if (lane == 0) {
       for (uint32_t s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+      for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -85,21 +93,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // this CTA's contiguous job range
+  // this CTA: member `member` of group `grp`; table tiles [vt0, vt1) in every round
   const int grp = blockIdx.x / p.g, member = blockIdx.x % p.g;
-  const long long j0 = (long long)grp * p.jpg;
-  const long long j1 = (j0 + p.jpg < p.total_jobs) ? j0 + p.jpg : p.total_jobs;
-  const int rg_first = (int)(j0 / p.num_vt);
-  const int vt_first = (int)(j0 % p.num_vt);
+  const int vt0 = grp * p.tpc;
+  const int vt1 = min(p.num_vt, vt0 + p.tpc);
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      int rg = rg_first, vt = vt_first;
-      for (long long j = j0; j < j1; ++j) {
-        const int rb = rg * p.g + member;
-        if (rb < p.num_rb) {
+      for (int round = 0; round < p.rounds; ++round) {
+        const int rb = round * p.g + member;
+        if (rb >= p.num_rb) break;
+        for (int vt = vt0; vt < vt1; ++vt) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), kStageBytes);
@@ -109,7 +115,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
-        if (++vt == p.num_vt) { vt = 0; ++rg; }
       }
     }
   } else if (warp == 1) {
@@ -117,10 +122,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      int rg = rg_first, vt = vt_first;
-      for (long long j = j0; j < j1; ++j) {
-        const int rb = rg * p.g + member;
-        if (rb < p.num_rb) {
+      for (int round = 0; round < p.rounds; ++round) {
+        const int rb = round * p.g + member;
+        if (rb >= p.num_rb) break;
+        for (int vt = vt0; vt < vt1; ++vt) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this stage
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kBlockN;
@@ -139,65 +144,89 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           umma_commit(tfull_bar(acc));                // accumulator complete
           acc ^= 1u; if (acc == 0) acc_phase ^= 1u;
         }
-        if (++vt == p.num_vt) { vt = 0; ++rg; }
       }
     }
   } else {
     // ============================ epilogue ================================
     const int quarter = warp & 3;                      // TMEM lanes this warp may read
+    const int half = (warp - 2) >> 2;                  // column half of every tile
     const int row_in_tile = quarter * 32 + lane;
-    uint32_t acc = 0, acc_phase = 0;
-    int rg = rg_first, vt = vt_first;
+    uint32_t acc = 0, acc_phase = 0, tb = 0;
     RowState st;
-    bool open = false;
     float rs = 1.f, a = kLog2e;
     int lab_local = -1;
     long long row = 0;
     int slot = 0;
     uint2* warp_buf = nullptr;
-    for (long long j = j0; j < j1; ++j) {
-      const int rb = rg * p.g + member;
-      const bool last_of_rg = (vt == p.num_vt - 1) || (j == j1 - 1);
-      if (rb < p.num_rb) {
-        if (!open) {
-          slot = blockIdx.x * p.max_seg + (rg - rg_first);
-          uint2* slot_buf = p.sv.cand + (size_t)slot * kBlockM * kCandCap;
-          st.reset(slot_buf + (size_t)row_in_tile * kCandCap);
-          warp_buf = slot_buf + (size_t)(quarter * 32) * kCandCap;
-          row = (long long)rb * kBlockM + row_in_tile;
-          rs = ((row < p.Q && p.inv_q) ? p.inv_q[row] : 1.f) * p.scale;
-          a = rs * kLog2e;
-          lab_local = -1;
-          if (p.labels && row < p.Q) {
-            const long long lg = p.labels[row];
-            const long long l = lg - p.index_base;
-            if (lg != -100 && l >= 0 && l < p.V) lab_local = (int)l;
-          }
-          open = true;
+    // Per-table-row scales of a tile: global -> registers one tile ahead -> a warp-private
+    // shared-memory copy (broadcast reads).  Warp-private so that the four epilogue warps
+    // never wait for one another: a warp busy compacting must not stall the other three.
+    constexpr int kHalfN = kBlockN / 2;
+    float* cs_warp = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + kBarBytes) +
+                     (warp - 2) * 2 * kHalfN;
+    float4 cs_ra = make_float4(1.f, 1.f, 1.f, 1.f);
+    int cs_vt = -1;
+    auto load_cs = [&](int vt_) {                      // lane l: this half's columns 4l..4l+3
+      const int c0 = vt_ * kBlockN + half * kHalfN + 4 * lane;
+      if (c0 + 3 < p.V) cs_ra = __ldg(reinterpret_cast<const float4*>(p.inv_t + c0));
+      else cs_ra = make_float4(c0 < p.V ? p.inv_t[c0] : 1.f, c0 + 1 < p.V ? p.inv_t[c0 + 1] : 1.f,
+                               c0 + 2 < p.V ? p.inv_t[c0 + 2] : 1.f, 1.f);
+      cs_vt = vt_;
+    };
+    for (int round = 0; round < p.rounds; ++round) {
+      const int rb = round * p.g + member;
+      if (rb >= p.num_rb || vt0 >= vt1) break;
+      slot = (rb * p.ng + grp) * 2 + half;
+      uint2* slot_buf = p.sv.cand + (size_t)slot * kBlockM * kCandCap;
+      st.reset(slot_buf + (size_t)row_in_tile * kCandCap);
+      warp_buf = slot_buf + (size_t)(quarter * 32) * kCandCap;
+      row = (long long)rb * kBlockM + row_in_tile;
+      if (row >= p.Q) st.tau = INFINITY;                // padding rows never append / compact
+      rs = ((row < p.Q && p.inv_q) ? p.inv_q[row] : 1.f) * p.scale;
+      a = rs * kLog2e;
+      lab_local = -1;
+      if (p.labels && row < p.Q) {
+        const long long lg = p.labels[row];
+        const long long l = lg - p.index_base;
+        if (lg != -100 && l >= 0 && l < p.V) lab_local = (int)l;
+      }
+      // threshold word shared by the ng CTAs that scan this query row (other table chunks)
+      uint32_t* tau_pub = p.tau_shared ? p.tau_shared + row : nullptr;
+      uint32_t tau_seen = 0u;
+      const bool more_rounds = (round + 1 < p.rounds) && ((round + 1) * p.g + member < p.num_rb);
+      for (int vt = vt0; vt < vt1; ++vt) {
+        if (p.inv_t) {
+          if (cs_vt != vt) load_cs(vt);                // first tile of a run: exposed once
+          reinterpret_cast<float4*>(cs_warp + tb * kHalfN)[lane] = cs_ra;
+          __syncwarp();
+          if (vt + 1 < vt1) load_cs(vt + 1); else if (more_rounds) load_cs(vt0);
+        }
+        if (tau_pub) {                                 // value read one tile ago, then re-read
+          row_apply_shared_tau(st, tau_seen);
+          tau_seen = __ldcg(tau_pub);
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN;
-        const int tile_col0 = vt * kBlockN;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / kChunk; ++c) {
-          const int col0 = tile_col0 + c * kChunk;
-          if (col0 >= p.V) break;                       // warp-uniform
-          float y[kChunk];
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kHalfN;
+        const int tile_col0 = vt * kBlockN + half * kHalfN;   // first column of this warp's half
+        const int nch = max(0, min(kHalfN / kChunk, (p.V - tile_col0 + kChunk - 1) / kChunk));
+        const float* cs_tile = cs_warp + tb * kHalfN;
+
+        auto release_acc = [&]() {                     // every tcgen05.ld of this tile has landed
+          tc_fence_before();
           __syncwarp();
-          tmem_ld_32x32(taddr + c * kChunk, y);
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        };
+        auto consume = [&](float (&y)[kChunk], int c) {
+          const int col0 = tile_col0 + c * kChunk;
           const int n_valid = min(kChunk, p.V - col0);
           if (p.inv_t) {
-            if (n_valid == kChunk) {
-              const float4* cs4 = reinterpret_cast<const float4*>(p.inv_t + col0);
+            const float4* cs4 = reinterpret_cast<const float4*>(cs_tile + c * kChunk);
 #pragma unroll
-              for (int i = 0; i < kChunk / 4; ++i) {
-                const float4 cs = __ldg(cs4 + i);
-                y[4 * i] *= cs.x; y[4 * i + 1] *= cs.y; y[4 * i + 2] *= cs.z; y[4 * i + 3] *= cs.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < kChunk; ++i) y[i] *= (i < n_valid) ? __ldg(p.inv_t + col0 + i) : 1.f;
+            for (int i = 0; i < kChunk / 4; ++i) {
+              const float4 cs = cs4[i];
+              y[4 * i] *= cs.x; y[4 * i + 1] *= cs.y; y[4 * i + 2] *= cs.z; y[4 * i + 3] *= cs.w;
             }
           }
           if (p.dbg_scores && row < p.Q) {
@@ -208,23 +237,37 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           if (n_valid == kChunk) row_process_chunk<false>(st, y, col0, kChunk, a, lab_local);
           else row_process_chunk<true>(st, y, col0, n_valid, a, lab_local);
           __syncwarp();
-          warp_compact_rows(st, p.k, warp_buf, lane);
+          warp_compact_rows(st, p.k, warp_buf, lane, tau_pub);
+        };
+
+        // TMEM -> registers, double buffered: chunk c+1 is in flight while chunk c is reduced
+        float ya[kChunk], yb[kChunk];
+        if (nch > 0) tmem_ld_issue(taddr, ya); else release_acc();   // half beyond the table's end
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait(ya);
+          if (c + 1 < nch) tmem_ld_issue(taddr + (c + 1) * kChunk, yb); else release_acc();
+          consume(ya, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait(yb);
+            if (c + 2 < nch) tmem_ld_issue(taddr + (c + 2) * kChunk, ya); else release_acc();
+            consume(yb, c + 1);
+          }
         }
-        // hand the accumulator stage back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
         acc ^= 1u; if (acc == 0) acc_phase ^= 1u;
-        if (last_of_rg) {
-          row_flush(st, rs, p.sv.cnt + (size_t)slot * kBlockM + row_in_tile,
-                    p.sv.stats + (size_t)slot * kBlockM + row_in_tile);
-          open = false;
-        }
+        tb ^= 1u;
       }
-      if (++vt == p.num_vt) { vt = 0; ++rg; }
+      row_flush(st, rs, p.sv.cnt + (size_t)slot * kBlockM + row_in_tile,
+                p.sv.stats + (size_t)slot * kBlockM + row_in_tile);
     }
   }
 
+  if (p.timing && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.timing[2 * blockIdx.x] = t_start;
+    p.timing[2 * blockIdx.x + 1] = t1;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -244,46 +287,55 @@ TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int f
   s.num_vt = (int)((V + kBlockN - 1) / kBlockN);
   s.num_kb = (int)((D + kBlockK - 1) / kBlockK);
   const int ctas = (force_ctas > 0) ? std::min(force_ctas, sm_count) : sm_count;
-  // Cost model per candidate g: tensor time ~ jobs per group; HBM time ~ one table pass per
-  // row-group (members of a group share tiles through L2; groups do not).
-  const double t_tile = 2.0 * kBlockM * kBlockN * (double)s.num_kb * kBlockK / 9.0e12;  // s, per-SM ~9 TF/s
+  // Cost model (fitted to B200 measurements, profiles/): time = tensor time of the longest CTA
+  // + HBM traffic / bandwidth.  Traffic = one table pass per round, plus the share of the
+  // L2-level operand traffic that misses once the working set (g query blocks + ng table
+  // streams of ~4 tiles) outgrows the usable L2.
+  const double a_block = (double)kBlockM * s.num_kb * kBlockK * 2.0;
+  const double b_tile = (double)kBlockN * s.num_kb * kBlockK * 2.0;
+  const double t_tile = 2.0 * kBlockM * kBlockN * (double)s.num_kb * kBlockK / 9.0e12;
   const double table_bytes = (double)V * (double)D * 2.0;
+  const double l2_level = (double)s.num_rb * s.num_vt * (a_block + b_tile);
+  const double l2_cap = 100.0e6, hbm_bw = 5.0e12, t_restart = 2.0e-6;
   double best = 1e300;
   int best_g = 1;
   const int gmax = std::max(1, std::min(s.num_rb, ctas));
   for (int g = 1; g <= gmax; ++g) {
-    const int ng = ctas / g;
+    const int ng = std::min(ctas / g, s.num_vt);
     if (ng < 1) break;
-    const long long num_rg = (s.num_rb + g - 1) / g;
-    const long long total = num_rg * s.num_vt;
-    const long long jpg = (total + ng - 1) / ng;
-    const double t_mma = (double)jpg * t_tile;
-    const double t_hbm = (double)num_rg * table_bytes / 5.5e12;
-    const double cost = std::max(t_mma, t_hbm) + 0.15 * t_hbm;
-    if (cost < best * 0.999 || (cost <= best * 1.001 && g > best_g)) { best = std::min(best, cost); best_g = g; }
+    const int rounds = (s.num_rb + g - 1) / g;
+    const int tpc = (s.num_vt + ng - 1) / ng;
+    const double ws = g * a_block + ng * 4.0 * b_tile;
+    const double miss = ws > l2_cap ? 1.0 - l2_cap / ws : 0.0;
+    const double dram = rounds * table_bytes + (double)Q * D * 2.0 + miss * l2_level;
+    const double cost = rounds * (tpc * t_tile + t_restart) + dram / hbm_bw;
+    if (cost < best) { best = cost; best_g = g; }
   }
   s.g = (force_g > 0) ? std::min(force_g, gmax) : best_g;
-  s.num_groups = std::max(1, ctas / s.g);
-  s.num_rg = (s.num_rb + s.g - 1) / s.g;
-  s.total_jobs = (long long)s.num_rg * s.num_vt;
-  s.jpg = (int)((s.total_jobs + s.num_groups - 1) / s.num_groups);
-  if (s.jpg < 1) s.jpg = 1;
-  s.max_seg = (s.jpg + s.num_vt - 1) / s.num_vt + 1;
-  s.grid = s.num_groups * s.g;
+  s.ng = std::max(1, std::min(ctas / s.g, s.num_vt));
+  s.rounds = (s.num_rb + s.g - 1) / s.g;
+  s.tpc = (s.num_vt + s.ng - 1) / s.ng;
+  s.ng = (s.num_vt + s.tpc - 1) / s.tpc;      // drop groups that would own no tile
+  s.grid = s.ng * s.g;
   return s;
 }
 
-Workspace carve_workspace(void* base, int nslots) {
+Workspace carve_workspace(void* base, int nslots, int num_rb) {
   Workspace w{};
   w.nslots = nslots;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_time = take(2 * 1024 * sizeof(unsigned long long));   // always at offset 0
+  const size_t o_tau = take((size_t)num_rb * kBlockM * sizeof(uint32_t));
   const size_t o_cand = take((size_t)nslots * kBlockM * kCandCap * sizeof(uint2));
   const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int));
   const size_t o_stats = take((size_t)nslots * kBlockM * sizeof(float4));
   w.bytes = off;
   if (base) {
     uint8_t* b = (uint8_t*)base;
+    w.timing = (void*)(b + o_time);
+    w.tau_shared = (void*)(b + o_tau);
+    w.tau_bytes = (size_t)num_rb * kBlockM * sizeof(uint32_t);
     w.sv.cand = (uint2*)(b + o_cand);
     w.sv.cnt = (int*)(b + o_cnt);
     w.sv.stats = (float4*)(b + o_stats);
@@ -341,10 +393,11 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   TcParams p{};
   p.Q = (int)a.Q; p.V = (int)a.V; p.D = (int)a.D; p.k = a.k;
   p.num_rb = sch.num_rb; p.num_vt = sch.num_vt; p.num_kb = sch.num_kb;
-  p.g = sch.g; p.jpg = sch.jpg; p.max_seg = sch.max_seg; p.total_jobs = sch.total_jobs;
+  p.g = sch.g; p.ng = sch.ng; p.rounds = sch.rounds; p.tpc = sch.tpc;
   p.inv_q = a.inv_q; p.inv_t = a.inv_t; p.scale = a.scale;
   p.index_base = a.index_base; p.labels = (const long long*)a.labels;
-  p.sv = sv; p.dbg_scores = a.dbg_scores;
+  p.sv = sv; p.dbg_scores = a.dbg_scores; p.timing = (unsigned long long*)a.timing;
+  p.tau_shared = (uint32_t*)a.tau_shared;
   scan_tc_kernel<<<sch.grid, kTcThreads, kTcSmemBytes, s>>>(tm_q, tm_t, p);
   return cudaGetLastError();
 }

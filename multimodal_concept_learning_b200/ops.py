@@ -219,7 +219,7 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
     log-sum-exp / cross-entropy statistics, without materialising the [Q,V] scores.
     ``normalize_*`` select cosine (True) vs raw dot product (False); a cached
     ``inv_norm_t`` (from :func:`row_inv_norm`) avoids re-reading the table."""
-    dev = _require_cuda(q, table, labels, inv_norm_q, inv_norm_t)
+    dev = _require_cuda(q, table, inv_norm_q, inv_norm_t)      # labels may arrive on the host
     if q.dtype != table.dtype:
         raise TypeError(f"q ({q.dtype}) and table ({table.dtype}) must have the same dtype")
     _dtype_code(q)
@@ -251,7 +251,8 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
 
 
 def concept_scan_debug(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv_norm_t=None,
-                       scale: float = 1.0, labels=None, index_base: int = 0):
+                       scale: float = 1.0, labels=None, index_base: int = 0,
+                       label_smoothing: float = 0.0):
     """Test hook: the same kernels, additionally dumping the score matrix [Q,V]."""
     lib = load()
     dev = _require_cuda(q, table)
@@ -274,7 +275,42 @@ def concept_scan_debug(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv
                                          _ptr(labels), val.data_ptr(), idx.data_ptr(),
                                          stats.data_ptr(), ws.data_ptr(), ws_bytes,
                                          scores.data_ptr(), _stream(dev)))
-    return ScanOutput(val, idx, stats, V, labels), scores
+    return ScanOutput(val, idx, stats, V, labels, float(label_smoothing)), scores
+
+
+def concept_scan_cta_times(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv_norm_t=None,
+                           scale: float = 1.0):
+    """Profiling hook: run the tcgen05 scan once with per-CTA globaltimer stamps and return a
+    [grid, 2] int64 CPU tensor of (start, end) nanoseconds."""
+    import ctypes as C
+    lib = load()
+    dev = _require_cuda(q, table)
+    q, table = _rowmajor(q), _rowmajor(table)
+    Q, D = q.shape
+    V = table.shape[0]
+    code = _dtype_code(q)
+    plan = (C.c_int32 * 10)()
+    with torch.cuda.device(dev):
+        sm = device_info()[0]
+        check(lib.mcl_plan_scan(Q, V, D, sm, plan))
+        grid = plan[8]
+        val = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
+        ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
+        ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+        old = lib.mcl_set_option(3, 1)
+        try:
+            check(lib.mcl_concept_scan(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
+                                       table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t), float(scale),
+                                       k, 0, None, val.data_ptr(), idx.data_ptr(), stats.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, _stream(dev)))
+        finally:
+            lib.mcl_set_option(3, old)
+        torch.cuda.synchronize(dev)
+    t = ws[: grid * 16].view(torch.int64).reshape(grid, 2).cpu()
+    return t, {k_: int(v) for k_, v in zip(
+        ["num_rb", "num_vt", "num_kb", "g", "ng", "rounds", "tpc", "nslots", "grid", "_"], plan)}
 
 
 @torch.library.custom_op("mcl::similarity_matrix", mutates_args=(), device_types="cuda")

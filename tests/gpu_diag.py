@@ -18,6 +18,7 @@ sys.path.insert(0, ROOT)
 
 STAGES = ["info", "rowops", "merge", "simt", "tc_tile", "tc_small", "tc_ragged", "tc_ties",
           "tc_perf"]
+# extra stages, run by name: sched (schedule sweep + per-CTA timing)
 
 
 def _imports():
@@ -206,6 +207,48 @@ def stage_tc_perf():
         same = (ti.sort(1).values == out.topk_idx[sub].sort(1).values).float().mean()
         print(f"[perf] top-50 index agreement with torch fp32 on 64 rows: {float(same):.4f}; "
               f"lse max err {float((torch.logsumexp(z,1) - out.lse[sub]).abs().max()):.2e}")
+
+
+def _time_scan(torch, mcl, q, t, inv_q, inv_t, n=5, scale=1.0):
+    for _ in range(2):
+        mcl.concept_scan(q, t, 50, inv_norm_q=inv_q, inv_norm_t=inv_t, scale=scale)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        mcl.concept_scan(q, t, 50, inv_norm_q=inv_q, inv_norm_t=inv_t, scale=scale)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def stage_sched():
+    """Schedule sweep: group size g and CTA count vs time, plus per-CTA busy-time spread."""
+    torch, mcl, ref = _imports()
+    from multimodal_concept_learning_b200.ops import concept_scan_cta_times
+    shapes = {"c3": (8192, 152064, 3584), "c2": (4096, 49408, 768), "c1": (16, 50257, 768),
+              "c3/8": (8192, 19008, 3584), "c4": (65536, 128256, 4096), "c5": (32768, 1048576, 1024)}
+    for name, (Q, V, D) in shapes.items():
+        q = torch.randn(Q, D, device="cuda").bfloat16()
+        t = torch.randn(V, D, device="cuda").bfloat16()
+        inv_q, inv_t = mcl.row_inv_norm(q), mcl.row_inv_norm(t)
+        ms = _time_scan(torch, mcl, q, t, inv_q, inv_t)
+        times, plan = concept_scan_cta_times(q, t, 50, inv_norm_q=inv_q, inv_norm_t=inv_t)
+        dur = (times[:, 1] - times[:, 0]).double() / 1e3
+        span = float(times[:, 1].max() - times[:, 0].min()) / 1e3
+        print(f"[sched {name}] heuristic g={plan['g']} ng={plan['ng']} rounds={plan['rounds']} tpc={plan['tpc']}: {ms:.3f} ms "
+              f"({2.0*Q*V*D/ms/1e9:.0f} TF/s); CTA busy us min/mean/max = {float(dur.min()):.0f}/{float(dur.mean()):.0f}/{float(dur.max()):.0f}, span {span:.0f}")
+        gs = {"c3": [8, 16, 21, 32, 64], "c3/8": [8, 16, 32, 64], "c4": [37, 49, 74, 148], "c5": [18, 37, 74],
+              "c2": [4, 8, 16, 32], "c1": [1]}[name]
+        for g in gs:
+            if g > (Q + 127) // 128:
+                continue
+            mcl.set_option(1, g)
+            ms = _time_scan(torch, mcl, q, t, inv_q, inv_t, n=3)
+            print(f"[sched {name}] g={g:3d}: {ms:.3f} ms ({2.0*Q*V*D/ms/1e9:.0f} TF/s)")
+        mcl.set_option(1, 0)
+        del q, t
+        torch.cuda.empty_cache()
 
 
 def main():

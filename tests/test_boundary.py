@@ -85,7 +85,7 @@ def test_argument_validation_needs_no_device(lib_built):
 def _plan(lib, Q, V, D, sm=148):
     out = (C.c_int32 * 10)()
     assert lib.mcl_plan_scan(Q, V, D, sm, out) == 0
-    keys = ["num_rb", "num_vt", "num_kb", "g", "num_groups", "num_rg", "jpg", "max_seg", "grid", "total_jobs"]
+    keys = ["num_rb", "num_vt", "num_kb", "g", "ng", "rounds", "tpc", "nslots", "grid", "_"]
     return dict(zip(keys, list(out)))
 
 
@@ -94,38 +94,38 @@ def _plan(lib, Q, V, D, sm=148):
                                    (1, 1, 8), (129, 257, 72), (700, 3000, 64)])
 @pytest.mark.parametrize("sm", [148, 5])
 def test_schedule_covers_every_tile_once(lib_built, shape, sm):
-    """Python restatement of the kernel's job walk and of merge.cu's slot map."""
+    """Python restatement of the kernel's round/chunk walk and of merge.cu's slot map."""
     from multimodal_concept_learning_b200 import _lib
     lib = _lib.load()
     Q, V, D = shape
     p = _plan(lib, Q, V, D, sm)
     assert p["num_rb"] == -(-Q // 128) and p["num_vt"] == -(-V // 256) and p["num_kb"] == -(-D // 64)
-    assert 1 <= p["grid"] <= sm and p["grid"] == p["num_groups"] * p["g"]
-    assert p["total_jobs"] == p["num_rg"] * p["num_vt"] and p["jpg"] * p["num_groups"] >= p["total_jobs"]
-    g, jpg, nvt, mseg = p["g"], p["jpg"], p["num_vt"], p["max_seg"]
-    if p["grid"] * p["max_seg"] > 5000 or p["total_jobs"] * g > 3_000_000:
-        pytest.skip("walk too long for a CPU test; arithmetic identical to smaller cases")
-    # kernel side: which (row block, tile) lands in which slot
-    written = {}
+    assert 1 <= p["grid"] <= sm and p["grid"] == p["ng"] * p["g"]
+    assert p["rounds"] * p["g"] >= p["num_rb"] and p["ng"] * p["tpc"] >= p["num_vt"]
+    assert (p["ng"] - 1) * p["tpc"] < p["num_vt"], "a group without tiles would leave its slots unwritten"
+    assert p["nslots"] == p["num_rb"] * p["ng"] * 2      # two column halves per (row block, chunk)
+    g, ng, tpc, nvt = p["g"], p["ng"], p["tpc"], p["num_vt"]
+    tiles = {}
     for cta in range(p["grid"]):
         grp, member = divmod(cta, g)
-        j0, j1 = grp * jpg, min((grp + 1) * jpg, p["total_jobs"])
-        rg_first = j0 // nvt
-        for j in range(j0, j1):
-            rg, vt = divmod(j, nvt)
-            rb = rg * g + member
-            if rb < p["num_rb"]:
-                slot = cta * mseg + (rg - rg_first)
-                assert rg - rg_first < mseg
-                written.setdefault((rb, slot), []).append(vt)
-    # merge side: slots enumerated per row block
+        for rnd in range(p["rounds"]):
+            rb = rnd * g + member
+            if rb >= p["num_rb"]:
+                break
+            for half in (0, 1):                          # warps 2-5 / 6-9: columns 0-127 / 128-255
+                slot = (rb * ng + grp) * 2 + half
+                assert slot not in tiles, "two CTAs write one slot"
+                tiles[slot] = (rb, half, list(range(grp * tpc, min(nvt, (grp + 1) * tpc))))
+    assert len(tiles) == p["nslots"]
+    nsplit = ng * 2                                     # merge side: slots rb*nsplit .. +nsplit-1
     for rb in range(p["num_rb"]):
-        rg, r = divmod(rb, g)
-        q0, q1 = (rg * nvt) // jpg, (rg * nvt + nvt - 1) // jpg
-        tiles = []
-        for q in range(q0, q1 + 1):
-            slot = (q * g + r) * mseg + (rg - (q * jpg) // nvt)
-            assert (rb, slot) in written, (rb, slot)
-            tiles += written.pop((rb, slot))
-        assert sorted(tiles) == list(range(nvt)), f"row block {rb} tiles not covered exactly once"
-    assert not written, "kernel writes a slot the merge never reads"
+        cover = {0: [], 1: []}
+        for i in range(nsplit):
+            owner, half, t = tiles[rb * nsplit + i]
+            assert owner == rb and t, "empty or foreign slot"
+            cover[half] += t
+        assert cover[0] == cover[1] == list(range(nvt)), f"row block {rb} tiles not covered exactly once"
+    # efficiency of the chosen schedule at full SM count: within 20% of perfect balance
+    if sm == 148 and p["num_rb"] * p["num_vt"] >= 148 * 8:
+        ideal = p["num_rb"] * p["num_vt"] / 148.0
+        assert p["rounds"] * p["tpc"] <= 1.2 * ideal + 1, p
