@@ -120,17 +120,18 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   int nsplit = 1;
   const int nslots = scan_nslots(Q, V, D, dtype, di.sm, &sch, &nsplit);
   const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
-  Workspace ws = carve_workspace(workspace, nslots, num_rb);
+  const int nctr = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.ng * sch.nwin : 0;
+  Workspace ws = carve_workspace(workspace, nslots, num_rb, nctr);
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
-             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared};
+             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr};
   int merge_split = 1;
   cudaError_t e;
   if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
     char msg[256] = "";
-    e = cudaMemsetAsync(ws.tau_shared, 0, ws.tau_bytes, stream);
+    e = cudaMemsetAsync(ws.tau_shared, 0, ws.zero_bytes, stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset of the shared thresholds");
     e = launch_scan_tc(a, sch, ws.sv, stream, msg, sizeof(msg));
     if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);
@@ -254,8 +255,10 @@ size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, in
   DevInfo di;
   if (!dev_info(&di)) { cudaGetLastError(); di.sm = 148; }
   if (Q <= 0 || V_local <= 0 || D <= 0) return 256;
-  const int nslots = scan_nslots(Q, V_local, D, dtype, di.sm, nullptr, nullptr);
-  return carve_workspace(nullptr, nslots, (int)((Q + kBlockM - 1) / kBlockM)).bytes;
+  TcSchedule sch{};
+  const int nslots = scan_nslots(Q, V_local, D, dtype, di.sm, &sch, nullptr);
+  const int nctr = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.ng * sch.nwin : 0;
+  return carve_workspace(nullptr, nslots, (int)((Q + kBlockM - 1) / kBlockM), nctr).bytes;
 }
 
 int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
@@ -404,7 +407,7 @@ int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* 
   if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || !plan_out) return fail(MCL_ERR_BAD_ARG, "bad plan args");
   const TcSchedule s = make_tc_schedule(Q, V_local, D, sm_count, (int)g_opt_ctas.load(), (int)g_opt_g.load());
   const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.ng, s.rounds, s.tpc, s.num_rb * s.ng * 2,
-                         s.grid, 0};
+                         s.grid, s.win};
   for (int i = 0; i < 10; ++i) plan_out[i] = v[i];
   return MCL_OK;
 }

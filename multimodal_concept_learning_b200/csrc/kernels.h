@@ -20,6 +20,7 @@ struct ScanArgs {
   float* dbg_scores;         // nullable, [Q,V]
   void* timing;              // nullable, [grid][2] uint64 (tcgen05 scan only)
   void* tau_shared;          // nullable, [num_rb*128] uint32 zeroed before launch (tcgen05 scan)
+  void* sync_ctr;            // [rounds*ng*nwin] int zeroed before launch (tcgen05 scan)
 };
 
 // Tile schedule of the tcgen05 scan (see scan_tc.cu): ng groups of g CTAs; in round r member m
@@ -27,6 +28,7 @@ struct ScanArgs {
 struct TcSchedule {
   int num_rb, num_vt, num_kb;
   int g, ng, rounds, tpc, grid;
+  int win, nwin;   // drift bound: members of a group stay within ~2 windows of `win` tiles
 };
 TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
                             int force_g);
@@ -34,13 +36,14 @@ TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int f
 struct Workspace {
   void* timing;   // [1024][2] uint64 at offset 0: per-CTA globaltimer start/end (debug option 3)
   void* tau_shared;   // one threshold word per (padded) query row, shared between CTAs
-  size_t tau_bytes;
+  void* sync_ctr;     // window-arrival counters of the tile scheduler (follow tau_shared)
+  size_t zero_bytes;  // tau_shared + sync_ctr: cleared before every scan
   SlotView sv;
   int nslots;
   size_t bytes;
 };
 // carve `nslots` slots out of a caller buffer (base may be null to only size it)
-Workspace carve_workspace(void* base, int nslots, int num_rb);
+Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr);
 
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen);

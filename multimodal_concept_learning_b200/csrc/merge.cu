@@ -66,9 +66,9 @@ struct TopList {
 // top-64; candidates that cannot beat the warp's current k-th key are dropped before any
 // sorting (after the first slot almost all are), survivors are batched 64 at a time through
 // a small shared-memory queue.  Warp 0 then folds the other warps' lists and writes the row.
-constexpr int kMergeWarps = 4;
 constexpr int kPendCap = 96;
 
+template <int kMergeWarps>
 __global__ void __launch_bounds__(32 * kMergeWarps)
 merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restrict__ inv_q,
                    float scale, long long index_base, float* __restrict__ topk_val,
@@ -103,6 +103,7 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
     if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
   }
 
+  const float rs = (inv_q ? inv_q[row] : 1.f) * scale;
   TopList top; top.init();
   unsigned long long kth = 0ull;          // key of the warp's current k-th best (0 = none yet)
   int npend = 0;
@@ -125,7 +126,9 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
     for (int base = 0; base < n; base += 32) {
       const int j = base + lane;
       unsigned long long key = 0ull;
-      if (j < n) { const uint2 e = b[j]; key = pack_key(__uint_as_float(e.x), e.y); }
+      // rank by the OUTPUT value z = y * rs (what callers and the rank merge see), so that
+      // scores whose z round to the same float tie-break by table row everywhere
+      if (j < n) { const uint2 e = b[j]; key = pack_key(__uint_as_float(e.x) * rs, e.y); }
       const bool keep = key > kth;        // keys are unique, so > loses nothing
       const unsigned km = __ballot_sync(0xffffffffu, keep);
       if (keep) q[npend + __popc(km & lt)] = key;
@@ -147,14 +150,13 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
   if (warp != 0) return;
   for (int w = 1; w < kMergeWarps; ++w) top.push(lists[w][lane], lists[w][32 + lane], lane);
 
-  const float rs = (inv_q ? inv_q[row] : 1.f) * scale;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int p = i * 32 + lane;
     const uint64_t key = i ? top.r1 : top.r0;
     if (p < k) {
       const bool empty = (key == 0ull);
-      topk_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32)) * rs;
+      topk_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32));
       topk_idx[(size_t)row * k + p] =
           empty ? -1ll : index_base + (long long)(uint32_t)(~(uint32_t)key);
     }
@@ -218,9 +220,15 @@ cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s) {
   if (Q == 0) return cudaSuccess;
-  merge_slots_kernel<<<(unsigned)Q, 32 * kMergeWarps, 0, s>>>(
-      sv, nsplit, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
-      (float4*)row_stats);
+  // few rows with many slots (small Q split over all SMs): more warps per row
+  if (nsplit > 32 && Q <= 4096)
+    merge_slots_kernel<16><<<(unsigned)Q, 32 * 16, 0, s>>>(
+        sv, nsplit, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
+        (float4*)row_stats);
+  else
+    merge_slots_kernel<4><<<(unsigned)Q, 32 * 4, 0, s>>>(
+        sv, nsplit, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
+        (float4*)row_stats);
   return cudaGetLastError();
 }
 

@@ -53,6 +53,8 @@ struct TcParams {
   float* dbg_scores;
   unsigned long long* timing;   // nullable: [grid][2] globaltimer at CTA start / end
   uint32_t* tau_shared;         // [num_rb*128] order-preserving keys, zeroed before the launch
+  int* sync_ctr;                // [rounds][ng][nwin] members that started a window, zeroed
+  int win, nwin;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -105,7 +107,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       for (int round = 0; round < p.rounds; ++round) {
         const int rb = round * p.g + member;
         if (rb >= p.num_rb) break;
+        const int members = min(p.g, p.num_rb - round * p.g);   // CTAs walking this chunk with me
+        int* ctr = p.sync_ctr + (size_t)(round * p.ng + grp) * p.nwin;
         for (int vt = vt0; vt < vt1; ++vt) {
+          // Drift bound: the g members of a group read the same table tiles and rely on L2 to
+          // fetch each from HBM once; nothing else keeps them together, and SMs differ in
+          // speed by a few percent.  A member announces every window of `win` tiles it starts
+          // and may not start window w before all members have started window w-2.
+          if ((vt - vt0) % p.win == 0) {
+            const int w = (vt - vt0) / p.win;
+            atomicAdd(ctr + w, 1);
+            if (w >= 2) {
+              const volatile int* c = ctr + (w - 2);
+              while (*c < members) __nanosleep(256);
+            }
+          }
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), kStageBytes);
@@ -317,25 +333,32 @@ TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int f
   s.tpc = (s.num_vt + s.ng - 1) / s.ng;
   s.ng = (s.num_vt + s.tpc - 1) / s.tpc;      // drop groups that would own no tile
   s.grid = s.ng * s.g;
+  // window of the drift bound: ~3 windows of every stream must fit in the L2 share left
+  // after the resident query blocks
+  const double l2_stream = std::max(8.0e6, 90.0e6 - s.g * a_block);
+  s.win = (int)std::max(1.0, std::min(16.0, l2_stream / (3.0 * b_tile * s.ng)));
+  s.nwin = (s.tpc + s.win - 1) / s.win;
   return s;
 }
 
-Workspace carve_workspace(void* base, int nslots, int num_rb) {
+Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
   Workspace w{};
   w.nslots = nslots;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_time = take(2 * 1024 * sizeof(unsigned long long));   // always at offset 0
   const size_t o_tau = take((size_t)num_rb * kBlockM * sizeof(uint32_t));
+  const size_t o_ctr = take((size_t)nctr * sizeof(int));
   const size_t o_cand = take((size_t)nslots * kBlockM * kCandCap * sizeof(uint2));
   const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int));
   const size_t o_stats = take((size_t)nslots * kBlockM * sizeof(float4));
   w.bytes = off;
+  w.zero_bytes = o_ctr + (((size_t)nctr * sizeof(int) + 255) & ~(size_t)255) - o_tau;
   if (base) {
     uint8_t* b = (uint8_t*)base;
     w.timing = (void*)(b + o_time);
     w.tau_shared = (void*)(b + o_tau);
-    w.tau_bytes = (size_t)num_rb * kBlockM * sizeof(uint32_t);
+    w.sync_ctr = (void*)(b + o_ctr);
     w.sv.cand = (uint2*)(b + o_cand);
     w.sv.cnt = (int*)(b + o_cnt);
     w.sv.stats = (float4*)(b + o_stats);
@@ -398,8 +421,20 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   p.index_base = a.index_base; p.labels = (const long long*)a.labels;
   p.sv = sv; p.dbg_scores = a.dbg_scores; p.timing = (unsigned long long*)a.timing;
   p.tau_shared = (uint32_t*)a.tau_shared;
-  scan_tc_kernel<<<sch.grid, kTcThreads, kTcSmemBytes, s>>>(tm_q, tm_t, p);
-  return cudaGetLastError();
+  p.sync_ctr = (int*)a.sync_ctr; p.win = sch.win; p.nwin = sch.nwin;
+  // Cooperative launch: the drift bound makes CTAs wait for one another, so all of them must
+  // be resident at once (grid <= SM count, one CTA per SM); the runtime checks exactly that.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sch.grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kTcSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, scan_tc_kernel, tm_q, tm_t, p);
 }
 
 }  // namespace mcl

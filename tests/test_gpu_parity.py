@@ -262,7 +262,12 @@ def test_full_size_properties_qwen2vl_scale(mcl):
     b = mcl.concept_scan(q, t[half:], k, inv_norm_t=inv_t[half:].clone(), index_base=half)
     mv, mi, ms = mcl.merge(torch.stack([a.topk_val, b.topk_val]), torch.stack([a.topk_idx, b.topk_idx]),
                            torch.stack([a.stats, b.stats]))
-    assert torch.equal(mi, full.topk_idx) and torch.equal(mv, full.topk_val)
+    assert torch.equal(mv, full.topk_val)                       # values bit-for-bit
+    # indices bit-for-bit, except among scores exactly equal to the k-th value (a boundary tie
+    # between distinct table rows may be resolved differently by the two chunkings)
+    differ = mi != full.topk_idx
+    assert not (differ & (mv != mv[:, -1:])).any()
+    assert float(differ.float().mean()) < 1e-4
     torch.testing.assert_close(ms[:, 0] + torch.log(ms[:, 1]), full.lse, rtol=1e-6, atol=1e-5)
     sub = slice(4000, 4032)
     z = torch.nn.functional.normalize(q[sub].float(), dim=1) @ torch.nn.functional.normalize(t.float(), dim=1).T
