@@ -16,7 +16,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0};
+std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -76,9 +76,9 @@ int simt_nsplit(int64_t Q, int64_t V, int sm) {
 int scan_nslots(int64_t Q, int64_t V, int64_t D, int dtype, int sm, TcSchedule* sch_out,
                 int* nsplit_out) {
   if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
-    TcSchedule s = make_tc_schedule(Q, V, D, sm, (int)g_opt_ctas.load(), (int)g_opt_g.load());
+    TcSchedule s = make_tc_schedule(Q, V, D, sm, (int)g_opt_ctas.load(), (int)g_opt_g.load(), (int)g_opt_cluster.load());
     if (sch_out) *sch_out = s;
-    return s.num_rb * s.ng * 2;   // two column halves per (row block, chunk)
+    return s.rounds * s.g * s.ng * 2;   // (padded row blocks) x chunks x two column halves
   }
   const int ns = simt_nsplit(Q, V, sm);
   if (nsplit_out) *nsplit_out = ns;
@@ -119,7 +119,8 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   TcSchedule sch{};
   int nsplit = 1;
   const int nslots = scan_nslots(Q, V, D, dtype, di.sm, &sch, &nsplit);
-  const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
+  const int num_rb = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.g
+                                                                     : (int)((Q + kBlockM - 1) / kBlockM);
   const int nctr = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.ng * sch.nwin : 0;
   Workspace ws = carve_workspace(workspace, nslots, num_rb, nctr);
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
@@ -258,7 +259,9 @@ size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, in
   TcSchedule sch{};
   const int nslots = scan_nslots(Q, V_local, D, dtype, di.sm, &sch, nullptr);
   const int nctr = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.ng * sch.nwin : 0;
-  return carve_workspace(nullptr, nslots, (int)((Q + kBlockM - 1) / kBlockM), nctr).bytes;
+  const int num_rb = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.g
+                                                                     : (int)((Q + kBlockM - 1) / kBlockM);
+  return carve_workspace(nullptr, nslots, num_rb, nctr).bytes;
 }
 
 int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
@@ -398,6 +401,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 1) return g_opt_g.exchange(value);
   if (opt == 2) return g_opt_simt.exchange(value);
   if (opt == 3) return g_opt_timing.exchange(value);
+  if (opt == 4) return g_opt_cluster.exchange(value);
   return -1;
 }
 
@@ -405,8 +409,8 @@ int64_t mcl_launch_count(void) { return g_launches.load(); }
 
 int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out) {
   if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || !plan_out) return fail(MCL_ERR_BAD_ARG, "bad plan args");
-  const TcSchedule s = make_tc_schedule(Q, V_local, D, sm_count, (int)g_opt_ctas.load(), (int)g_opt_g.load());
-  const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.ng, s.rounds, s.tpc, s.num_rb * s.ng * 2,
+  const TcSchedule s = make_tc_schedule(Q, V_local, D, sm_count, (int)g_opt_ctas.load(), (int)g_opt_g.load(), (int)g_opt_cluster.load());
+  const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.ng, s.rounds, s.tpc, s.rounds * s.g * s.ng * 2,
                          s.grid, s.win};
   for (int i = 0; i < 10; ++i) plan_out[i] = v[i];
   return MCL_OK;

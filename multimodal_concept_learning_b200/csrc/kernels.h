@@ -29,9 +29,10 @@ struct TcSchedule {
   int num_rb, num_vt, num_kb;
   int g, ng, rounds, tpc, grid;
   int win, nwin;   // drift bound: members of a group stay within ~2 windows of `win` tiles
+  int cluster;     // CTAs per cluster: 2 = pairs multicast the table tile halves, 1 = none
 };
 TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
-                            int force_g);
+                            int force_g, int force_cluster);
 
 struct Workspace {
   void* timing;   // [1024][2] uint64 at offset 0: per-CTA globaltimer start/end (debug option 3)

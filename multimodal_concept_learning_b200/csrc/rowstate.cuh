@@ -114,8 +114,7 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
   unsigned need = __ballot_sync(0xffffffffu, st.cnt + kChunk > kCandCap);
   if (need == 0) return;
   const unsigned lt = (1u << lane) - 1u;
-  __threadfence_block();
-  __syncwarp();  // the owners' appends are visible to the warp
+  __syncwarp();  // orders the owners' appends before the warp's reads (no fence needed)
   while (need) {
     const int r = __ffs(need) - 1;
     need &= need - 1;

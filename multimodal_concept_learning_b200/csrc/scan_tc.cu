@@ -29,16 +29,15 @@
 
 namespace mcl {
 
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 8;                          // two per TMEM lane quarter: column halves
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr uint32_t kBBytes = kBlockN * kBlockK * 2;   // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;   // 48 KB
+constexpr uint32_t kRingBytes = 192 * 1024;           // operand ring: 4 x 48 KB, or 6 x 32 KB per CTA of a pair
 constexpr uint32_t kTmemCols = 512;                   // 2 accumulator stages x 256 columns
 constexpr uint32_t kBarBytes = 256;
 constexpr uint32_t kCsBytes = kEpiWarps * 2 * (kBlockN / 2) * 4;  // per epilogue warp: 2 x 128 table-row scales
-constexpr uint32_t kTcSmemBytes = kStages * kStageBytes + kBarBytes + kCsBytes + 1024;  // + align slack
+constexpr uint32_t kTcSmemBytes = kRingBytes + kBarBytes + kCsBytes + 1024;  // + align slack
 
 struct TcParams {
   int Q, V, D, k;
@@ -57,12 +56,25 @@ struct TcParams {
   int win, nwin;
 };
 
+// kCS = CTAs per cluster.  kCS = 1: every CTA multiplies its own 128 x 256 tile
+// (cta_group::1, 48 KB of operands per K slice, 4 stages).  kCS = 2: two consecutive members of
+// a group (same table tiles, different query row blocks) form a CTA pair and ONE
+// tcgen05.mma.cta_group::2 (M = 256) issued by the even CTA multiplies both row blocks: each
+// CTA stages only its own A tile and HALF of the B tile (32 KB per K slice, 6 stages) and the
+// tensor core reads the B halves out of both CTAs' shared memory.  That cuts shared-memory
+// traffic (TMA writes + MMA reads) by a third -- the single-CTA tile is bound by it -- and each
+// CTA still finds its own 128 rows x 256 columns of accumulators in its own TMEM, so the
+// epilogue is identical.
+template <int kCS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_t,
                const TcParams p) {
+  constexpr uint32_t kStageBytes = kABytes + kBBytes / kCS;   // per CTA
+  constexpr uint32_t kStages = kRingBytes / kStageBytes;      // 4 or 6
+  constexpr uint32_t kSliceRows = kBlockN / kCS;              // table rows of a tile this CTA stages
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = smem_base + kRingBytes;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](uint32_t a) { return bar_base + 8u * (2 * kStages + a); };
@@ -70,7 +82,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8u * (2 * kStages + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kRingBytes + 8u * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long t_start = 0;
@@ -82,18 +94,23 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   }
   if (warp == 1) {
     if (lane == 0) {
+      // full: the (leader's) producer arms it; empty / tfull: one tcgen05.commit arrival;
+      // tempty: every epilogue warp of every CTA whose accumulators the MMA overwrites
       for (uint32_t s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+      for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps * kCS); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kCS == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    else { tmem_alloc_2sm(tmem_slot, kTmemCols); tmem_relinquish_2sm(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (kCS > 1) cluster_sync_all();      // the peer's barriers and TMEM exist before they are used
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t crank = (kCS > 1) ? cluster_ctarank() : 0u;
+  const bool leader = (crank == 0);
 
   // this CTA: member `member` of group `grp`; table tiles [vt0, vt1) in every round
   const int grp = blockIdx.x / p.g, member = blockIdx.x % p.g;
@@ -106,8 +123,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       uint32_t stage = 0, phase = 0;
       for (int round = 0; round < p.rounds; ++round) {
         const int rb = round * p.g + member;
-        if (rb >= p.num_rb) break;
-        const int members = min(p.g, p.num_rb - round * p.g);   // CTAs walking this chunk with me
+        if (round * p.g + (member / kCS) * kCS >= p.num_rb) break;   // whole cluster idle
+        // CTAs walking this chunk with me (clusters take part as a whole)
+        const int members = ((min(p.g, p.num_rb - round * p.g) + kCS - 1) / kCS) * kCS;
         int* ctr = p.sync_ctr + (size_t)(round * p.ng + grp) * p.nwin;
         for (int vt = vt0; vt < vt1; ++vt) {
           // Drift bound: the g members of a group read the same table tiles and rely on L2 to
@@ -124,10 +142,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           }
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), kStageBytes);
             const uint32_t sa = smem_base + stage * kStageBytes;
-            tma_load_2d(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM);
-            tma_load_2d(sa + kABytes, &tm_t, full_bar(stage), kb * kBlockK, vt * kBlockN);
+            if (kCS == 1) {
+              mbar_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_2d(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM);
+              tma_load_2d(sa + kABytes, &tm_t, full_bar(stage), kb * kBlockK, vt * kBlockN);
+            } else {
+              // both CTAs' bytes are counted on the leader's barrier, which its producer arms
+              if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+              tma_load_2d_2sm(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM);
+              tma_load_2d_2sm(sa + kABytes, &tm_t, full_bar(stage), kb * kBlockK,
+                              vt * kBlockN + (int)(crank * kSliceRows));
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -135,12 +161,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCS, kBlockN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int round = 0; round < p.rounds; ++round) {
-        const int rb = round * p.g + member;
-        if (rb >= p.num_rb) break;
+        if (round * p.g + (member / kCS) * kCS >= p.num_rb) break;
         for (int vt = vt0; vt < vt1; ++vt) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this stage
           tc_fence_after();
@@ -152,12 +177,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const uint64_t adesc = umma_desc_sw128(sa);
             const uint64_t bdesc = umma_desc_sw128(sa + kABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K=16 step inside the 128 B row
-              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
-            umma_commit(empty_bar(stage));            // smem slot reusable once the MMAs retire
+            for (int k = 0; k < kBlockK / 16; ++k) { // +32 B per K=16 step inside the 128 B row
+              if (kCS == 1) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+              else umma_bf16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            }
+            // smem slot reusable once the MMAs retire (in both CTAs of a pair)
+            if (kCS == 1) umma_commit(empty_bar(stage)); else umma_commit_2sm(empty_bar(stage));
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(tfull_bar(acc));                // accumulator complete
+          // accumulator complete (each CTA's epilogue waits on its own barrier)
+          if (kCS == 1) umma_commit(tfull_bar(acc)); else umma_commit_2sm(tfull_bar(acc));
           acc ^= 1u; if (acc == 0) acc_phase ^= 1u;
         }
       }
@@ -178,7 +207,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     // shared-memory copy (broadcast reads).  Warp-private so that the four epilogue warps
     // never wait for one another: a warp busy compacting must not stall the other three.
     constexpr int kHalfN = kBlockN / 2;
-    float* cs_warp = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + kBarBytes) +
+    float* cs_warp = reinterpret_cast<float*>(smem_gen + kRingBytes + kBarBytes) +
                      (warp - 2) * 2 * kHalfN;
     float4 cs_ra = make_float4(1.f, 1.f, 1.f, 1.f);
     int cs_vt = -1;
@@ -190,8 +219,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       cs_vt = vt_;
     };
     for (int round = 0; round < p.rounds; ++round) {
-      const int rb = round * p.g + member;
-      if (rb >= p.num_rb || vt0 >= vt1) break;
+      const int rb = round * p.g + member;          // may be a padding row block inside a cluster
+      if (round * p.g + (member / kCS) * kCS >= p.num_rb || vt0 >= vt1) break;
       slot = (rb * p.ng + grp) * 2 + half;
       uint2* slot_buf = p.sv.cand + (size_t)slot * kBlockM * kCandCap;
       st.reset(slot_buf + (size_t)row_in_tile * kCandCap);
@@ -209,7 +238,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       // threshold word shared by the ng CTAs that scan this query row (other table chunks)
       uint32_t* tau_pub = p.tau_shared ? p.tau_shared + row : nullptr;
       uint32_t tau_seen = 0u;
-      const bool more_rounds = (round + 1 < p.rounds) && ((round + 1) * p.g + member < p.num_rb);
+      const bool more_rounds =
+          (round + 1 < p.rounds) && ((round + 1) * p.g + (member / kCS) * kCS < p.num_rb);
       for (int vt = vt0; vt < vt1; ++vt) {
         if (p.inv_t) {
           if (cs_vt != vt) load_cs(vt);                // first tile of a run: exposed once
@@ -232,7 +262,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         auto release_acc = [&]() {                     // every tcgen05.ld of this tile has landed
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (kCS == 1 || leader) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_remote(tempty_bar(acc), 0);   // the MMA issuer lives in the leader
+          }
         };
         auto consume = [&](float (&y)[kChunk], int c) {
           const int col0 = tile_col0 + c * kChunk;
@@ -256,19 +289,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           warp_compact_rows(st, p.k, warp_buf, lane, tau_pub);
         };
 
-        // TMEM -> registers, double buffered: chunk c+1 is in flight while chunk c is reduced
-        float ya[kChunk], yb[kChunk];
-        if (nch > 0) tmem_ld_issue(taddr, ya); else release_acc();   // half beyond the table's end
+        // TMEM -> registers one chunk at a time; the other epilogue warp on this scheduler
+        // covers the load latency, and a single copy of the chunk code spares the I-cache
+        float y[kChunk];
+        if (nch == 0) release_acc();                   // this half lies beyond the table's end
 #pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-          tmem_ld_wait(ya);
-          if (c + 1 < nch) tmem_ld_issue(taddr + (c + 1) * kChunk, yb); else release_acc();
-          consume(ya, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait(yb);
-            if (c + 2 < nch) tmem_ld_issue(taddr + (c + 2) * kChunk, ya); else release_acc();
-            consume(yb, c + 1);
-          }
+        for (int c = 0; c < nch; ++c) {
+          __syncwarp();
+          tmem_ld_issue(taddr + c * kChunk, y);
+          tmem_ld_wait(y);
+          if (c + 1 == nch) release_acc();
+          consume(y, c);
         }
         acc ^= 1u; if (acc == 0) acc_phase ^= 1u;
         tb ^= 1u;
@@ -286,9 +317,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (kCS > 1) cluster_sync_all();      // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCS == 1) tmem_dealloc(tmem_base, kTmemCols); else tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
@@ -297,7 +329,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 // ---------------------------------------------------------------------------------------
 
 TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
-                            int force_g) {
+                            int force_g, int force_cluster) {
   TcSchedule s{};
   s.num_rb = (int)((Q + kBlockM - 1) / kBlockM);
   s.num_vt = (int)((V + kBlockN - 1) / kBlockN);
@@ -312,7 +344,10 @@ TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int f
   const double t_tile = 2.0 * kBlockM * kBlockN * (double)s.num_kb * kBlockK / 9.0e12;
   const double table_bytes = (double)V * (double)D * 2.0;
   const double l2_level = (double)s.num_rb * s.num_vt * (a_block + b_tile);
-  const double l2_cap = 100.0e6, hbm_bw = 5.0e12, t_restart = 2.0e-6;
+  const double l2_cap = 100.0e6, hbm_bw = 5.0e12;
+  // every round restarts the top-k filter of each row (threshold -inf -> bursts of buffer
+  // compactions while it tightens): measured 0.15-0.3 ms per round on B200
+  const double t_restart = 2.0e-4;
   double best = 1e300;
   int best_g = 1;
   const int gmax = std::max(1, std::min(s.num_rb, ctas));
@@ -324,10 +359,12 @@ TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int f
     const double ws = g * a_block + ng * 4.0 * b_tile;
     const double miss = ws > l2_cap ? 1.0 - l2_cap / ws : 0.0;
     const double dram = rounds * table_bytes + (double)Q * D * 2.0 + miss * l2_level;
-    const double cost = rounds * (tpc * t_tile + t_restart) + dram / hbm_bw;
+    double cost = rounds * (tpc * t_tile + t_restart) + dram / hbm_bw;
+    if (g % 2 != 0) cost *= 1.08;        // no CTA pairing: 48 instead of 32 KB per K slice from L2
     if (cost < best) { best = cost; best_g = g; }
   }
   s.g = (force_g > 0) ? std::min(force_g, gmax) : best_g;
+  s.cluster = (s.g % 2 == 0 && force_cluster != 1) ? 2 : 1;   // CTA pairs share table tiles
   s.ng = std::max(1, std::min(ctas / s.g, s.num_vt));
   s.rounds = (s.num_rb + s.g - 1) / s.g;
   s.tpc = (s.num_vt + s.ng - 1) / s.ng;
@@ -401,14 +438,18 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
                            cudaStream_t s, char* err, size_t errlen) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kTcSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kTcSmemBytes);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(smem=%u)", kTcSmemBytes); return e; }
     attr_set = true;
   }
+  const int cs = sch.cluster;
   CUtensorMap tm_q, tm_t;
   if (!make_tmap(&tm_q, a.q, a.Q, a.D, a.ldq, kBlockM) ||
-      !make_tmap(&tm_t, a.table, a.V, a.D, a.ldt, kBlockN)) {
+      !make_tmap(&tm_t, a.table, a.V, a.D, a.ldt, kBlockN / cs)) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (Q=%lld V=%lld D=%lld ldq=%lld ldt=%lld)",
              (long long)a.Q, (long long)a.V, (long long)a.D, (long long)a.ldq, (long long)a.ldt);
     return cudaErrorInvalidValue;
@@ -429,12 +470,19 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = kTcSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
+  if (cs == 2) {   // clusters: co-residency follows from grid <= SM count with one CTA per SM
+    cfg.attrs = attr + 1;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, scan_tc_kernel<2>, tm_q, tm_t, p);
+  }
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, scan_tc_kernel, tm_q, tm_t, p);
+  return cudaLaunchKernelEx(&cfg, scan_tc_kernel<1>, tm_q, tm_t, p);
 }
 
 }  // namespace mcl

@@ -103,7 +103,7 @@ def test_schedule_covers_every_tile_once(lib_built, shape, sm):
     assert 1 <= p["grid"] <= sm and p["grid"] == p["ng"] * p["g"]
     assert p["rounds"] * p["g"] >= p["num_rb"] and p["ng"] * p["tpc"] >= p["num_vt"]
     assert (p["ng"] - 1) * p["tpc"] < p["num_vt"], "a group without tiles would leave its slots unwritten"
-    assert p["nslots"] == p["num_rb"] * p["ng"] * 2      # two column halves per (row block, chunk)
+    assert p["nslots"] == p["rounds"] * p["g"] * p["ng"] * 2   # (padded row blocks) x chunks x column halves
     g, ng, tpc, nvt = p["g"], p["ng"], p["tpc"], p["num_vt"]
     tiles = {}
     for cta in range(p["grid"]):
@@ -116,7 +116,7 @@ def test_schedule_covers_every_tile_once(lib_built, shape, sm):
                 slot = (rb * ng + grp) * 2 + half
                 assert slot not in tiles, "two CTAs write one slot"
                 tiles[slot] = (rb, half, list(range(grp * tpc, min(nvt, (grp + 1) * tpc))))
-    assert len(tiles) == p["nslots"]
+    assert len(tiles) == p["num_rb"] * ng * 2
     nsplit = ng * 2                                     # merge side: slots rb*nsplit .. +nsplit-1
     for rb in range(p["num_rb"]):
         cover = {0: [], 1: []}
