@@ -115,22 +115,42 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
   if (need == 0) return;
   const unsigned lt = (1u << lane) - 1u;
   __syncwarp();  // orders the owners' appends before the warp's reads (no fence needed)
-  while (need) {
-    const int r = __ffs(need) - 1;
-    need &= need - 1;
-    const int n = __shfl_sync(0xffffffffu, st.cnt, r);
-    const uint32_t tau_key = f2key(__shfl_sync(0xffffffffu, st.tau, r));
+  // The reload of a row's entries is an L2 round trip (~2/3 of a compaction).  At the start of
+  // a table chunk all 32 rows of a warp fill up together, so the NEXT row's entries are
+  // requested before the current row is processed.
+  uint2 raw_next[kCandCap / 32];
+  int r_next = __ffs(need) - 1, n_next = 0;
+  uint32_t tau_next = 0u;
+  need &= need - 1;
+  auto request = [&](int r_) {                         // issue the loads of row r_ (no use yet)
+    n_next = __shfl_sync(0xffffffffu, st.cnt, r_);
+    tau_next = f2key(__shfl_sync(0xffffffffu, st.tau, r_));
+    const uint2* bp = warp_buf + (size_t)r_ * kCandCap;
+#pragma unroll
+    for (int i = 0; i < kCandCap / 32; ++i) {
+      const int j = lane + 32 * i;
+      raw_next[i] = make_uint2(0u, 0u);
+      if (j < n_next) raw_next[i] = __ldcg(bp + j);
+    }
+  };
+  request(r_next);
+  while (r_next >= 0) {
+    const int r = r_next;
+    const int n = n_next;
+    const uint32_t tau_key = tau_next;
     uint2* b = warp_buf + (size_t)r * kCandCap;
     uint32_t key[kCandCap / 32], idx[kCandCap / 32];
 #pragma unroll
     for (int i = 0; i < kCandCap / 32; ++i) {
       const int j = lane + 32 * i;
-      key[i] = 0u; idx[i] = 0u;                       // key 0 is below every real score
-      if (j < n) {
-        const uint2 e = __ldcg(b + j);
-        key[i] = f2key(__uint_as_float(e.x));
-        idx[i] = e.y;
-      }
+      key[i] = (j < n) ? f2key(__uint_as_float(raw_next[i].x)) : 0u;   // 0 is below every real score
+      idx[i] = raw_next[i].y;
+    }
+    r_next = -1;
+    if (need) {
+      r_next = __ffs(need) - 1;
+      need &= need - 1;
+      request(r_next);
     }
     // ---- bisection: x with k <= #{key >= x} <= k + kSlack ------------------------------
     uint32_t mx = key[0];
