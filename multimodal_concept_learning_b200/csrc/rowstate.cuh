@@ -116,42 +116,41 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
   const unsigned lt = (1u << lane) - 1u;
   __syncwarp();  // orders the owners' appends before the warp's reads (no fence needed)
   // The reload of a row's entries is an L2 round trip (~2/3 of a compaction).  At the start of
-  // a table chunk all 32 rows of a warp fill up together, so the NEXT row's entries are
-  // requested before the current row is processed.
-  uint2 raw_next[kCandCap / 32];
-  int r_next = __ffs(need) - 1, n_next = 0;
-  uint32_t tau_next = 0u;
-  need &= need - 1;
-  auto request = [&](int r_) {                         // issue the loads of row r_ (no use yet)
-    n_next = __shfl_sync(0xffffffffu, st.cnt, r_);
-    tau_next = f2key(__shfl_sync(0xffffffffu, st.tau, r_));
-    const uint2* bp = warp_buf + (size_t)r_ * kCandCap;
+  // a table chunk all 32 rows of a warp fill up together, so the entries of the next TWO rows
+  // are requested before the current row is processed.
+  struct Pending { uint2 raw[kCandCap / 32]; int r, n; uint32_t tau; };
+  auto fetch = [&](Pending& pd) {                      // pop a row and issue its loads (no use yet)
+    pd.r = -1; pd.n = 0; pd.tau = 0u;
 #pragma unroll
-    for (int i = 0; i < kCandCap / 32; ++i) {
-      const int j = lane + 32 * i;
-      raw_next[i] = make_uint2(0u, 0u);
-      if (j < n_next) raw_next[i] = __ldcg(bp + j);
+    for (int i = 0; i < kCandCap / 32; ++i) pd.raw[i] = make_uint2(0u, 0u);
+    if (need) {
+      pd.r = __ffs(need) - 1;
+      need &= need - 1;
+      pd.n = __shfl_sync(0xffffffffu, st.cnt, pd.r);
+      pd.tau = f2key(__shfl_sync(0xffffffffu, st.tau, pd.r));
+      const uint2* bp = warp_buf + (size_t)pd.r * kCandCap;
+#pragma unroll
+      for (int i = 0; i < kCandCap / 32; ++i)
+        if (lane + 32 * i < pd.n) pd.raw[i] = __ldcg(bp + lane + 32 * i);
     }
   };
-  request(r_next);
-  while (r_next >= 0) {
-    const int r = r_next;
-    const int n = n_next;
-    const uint32_t tau_key = tau_next;
+  Pending nx1, nx2;
+  fetch(nx1);
+  fetch(nx2);
+  while (nx1.r >= 0) {
+    const int r = nx1.r;
+    const int n = nx1.n;
+    const uint32_t tau_key = nx1.tau;
     uint2* b = warp_buf + (size_t)r * kCandCap;
     uint32_t key[kCandCap / 32], idx[kCandCap / 32];
 #pragma unroll
     for (int i = 0; i < kCandCap / 32; ++i) {
       const int j = lane + 32 * i;
-      key[i] = (j < n) ? f2key(__uint_as_float(raw_next[i].x)) : 0u;   // 0 is below every real score
-      idx[i] = raw_next[i].y;
+      key[i] = (j < n) ? f2key(__uint_as_float(nx1.raw[i].x)) : 0u;   // 0 is below every real score
+      idx[i] = nx1.raw[i].y;
     }
-    r_next = -1;
-    if (need) {
-      r_next = __ffs(need) - 1;
-      need &= need - 1;
-      request(r_next);
-    }
+    nx1 = nx2;
+    fetch(nx2);
     // ---- bisection: x with k <= #{key >= x} <= k + kSlack ------------------------------
     uint32_t mx = key[0];
 #pragma unroll
