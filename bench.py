@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -237,7 +237,7 @@ def cpu_sample_size(w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
@@ -301,7 +301,12 @@ def main():
     achieved = shard_flops / (res["ms_per_step"] * 1e-3) / 1e12
     out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                        "frac": achieved / pk["bf16_tflops"], "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],
-                       "peak_source": pk["source"] + " (burst cuBLAS bf16)", "traffic": None,
+                       "peak_source": pk["source"] + " (burst cuBLAS bf16)",
+                       # dram__bytes_read.sum + dram__bytes_write.sum of scan_tc_kernel<2>, one launch of this
+                       # workload at N=1, from profiles/r01_c3_scan_tc_v3_ncu_raw.csv (ncu --set full)
+                       "traffic": 4.949e9 if (args.workload == "c3" and world == 1) else None,
+                       "traffic_unit": "bytes per launch (algorithmic: %.3e)" % (
+                           2.0 * (w["V"] / world * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * K_TOP + 16)),
                        "kernel": "scan_tc_kernel (per GPU; step time includes the merge kernel)"}
     if world == 1 and rank == 0 and not args.profile:
         torch.set_num_threads(os.cpu_count() or 1)
