@@ -235,6 +235,16 @@ def cpu_sample_size(w):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner)
+    # are sent to stderr for the duration of the run
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -278,7 +288,7 @@ def main():
                                       "sample": f"{n} of {w['Q']} queries per step against the full table "
                                                 "(torch fp32 normalize->matmul->topk->logsumexp/CE)"},
                      "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base), flush=True)
+        emit(base)
         return
 
     if not torch.cuda.is_available():
@@ -333,7 +343,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 if __name__ == "__main__":
