@@ -51,6 +51,15 @@ struct TopList {
   uint64_t r0, r1;  // running top-64, descending over p = i*32 + lane
   __device__ __forceinline__ void init() { r0 = 0ull; r1 = 0ull; }
   // merge a batch of 64 unsorted keys (b0 = positions 0..31, b1 = 32..63)
+  // same, for a batch that is ALREADY sorted descending (another list, a rank's top-k):
+  // reverse + element-wise max + one 6-stage bitonic merge instead of a 21-stage sort
+  __device__ __forceinline__ void push_sorted(uint64_t b0, uint64_t b1, int lane) {
+    const uint64_t rb0 = shfl64(b1, 31 - lane);
+    const uint64_t rb1 = shfl64(b0, 31 - lane);
+    r0 = max64(r0, rb0);
+    r1 = max64(r1, rb1);
+    bitonic64_desc(r0, r1, lane, 64);
+  }
   __device__ __forceinline__ void push(uint64_t b0, uint64_t b1, int lane) {
     bitonic64_desc(b0, b1, lane, 2);
     // reversed batch: position p takes batch element 63 - p
@@ -148,7 +157,7 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
   lists[warp][32 + lane] = top.r1;
   __syncthreads();
   if (warp != 0) return;
-  for (int w = 1; w < kMergeWarps; ++w) top.push(lists[w][lane], lists[w][32 + lane], lane);
+  for (int w = 1; w < kMergeWarps; ++w) top.push_sorted(lists[w][lane], lists[w][32 + lane], lane);
 
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -201,7 +210,11 @@ merge_ranks_kernel(const char* __restrict__ val_b, const char* __restrict__ idx_
     uint64_t b0 = 0ull, b1 = 0ull;
     if (lane < k && ix[lane] >= 0) b0 = pack_key(v[lane], (uint32_t)ix[lane]);
     if (lane + 32 < k && ix[lane + 32] >= 0) b1 = pack_key(v[lane + 32], (uint32_t)ix[lane + 32]);
-    top.push(b0, b1, lane);
+    // a rank's list is sorted (value desc, row asc) by contract; verify cheaply, sort if not
+    const uint64_t nxt0 = shfl64(b0, (lane + 1) & 31), nxt1 = shfl64(b1, (lane + 1) & 31);
+    const uint64_t first1 = shfl64(b1, 0);
+    const bool ok = (lane == 31) ? (b0 >= first1) : (b0 >= nxt0 && b1 >= nxt1);
+    if (__all_sync(0xffffffffu, ok)) top.push_sorted(b0, b1, lane); else top.push(b0, b1, lane);
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {

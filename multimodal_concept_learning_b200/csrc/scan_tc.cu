@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <algorithm>
+#include <atomic>
 #include "rowstate.cuh"
 #include "kernels.h"
 
@@ -436,15 +437,18 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t c
 
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev].load()) {
     cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kTcSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)kTcSmemBytes);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(smem=%u)", kTcSmemBytes); return e; }
-    attr_set = true;
+    attr_set[dev].store(true);
   }
   const int cs = sch.cluster;
   CUtensorMap tm_q, tm_t;
