@@ -138,3 +138,30 @@ def test_a7_vision_head_shim_matches_golden():
     want, wpred, _ = S.vision_ce_top1_ref(feats.half().float(), w.half().float(), bias, labels, 0.1)
     assert abs(float(loss) - float(want)) <= 1e-4 * float(want)
     assert torch.equal(pred.cpu(), wpred)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("eps", [0.0, 0.1])
+def test_f1_fused_cross_entropy_backward_matches_autograd(dtype, rtol, eps):
+    """gradients of the fused CE w.r.t. hidden states and the (tied) table against
+    torch autograd through the reference formulation F.cross_entropy(h @ E^T)."""
+    from multimodal_concept_learning_b200.autograd import fused_cross_entropy
+    g = torch.Generator().manual_seed(50)
+    Q, V, D = 96, 3001, 64
+    h = (torch.randn(Q, D, generator=g) * 0.5).to(dtype).cuda().requires_grad_(True)
+    E = (torch.randn(V, D, generator=g) * 0.5).to(dtype).cuda().requires_grad_(True)
+    labels = torch.randint(0, V, (Q,), generator=g)
+    labels[::3] = -100
+    labels = labels.cuda()
+    loss, pred = fused_cross_entropy(h, E, labels, label_smoothing=eps, chunk_rows=1000)
+    loss.backward()
+    h2 = h.detach().double().requires_grad_(True)
+    E2 = E.detach().double().requires_grad_(True)
+    ref = F.cross_entropy(h2 @ E2.T, labels, ignore_index=-100, label_smoothing=eps)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    scale_h, scale_E = h2.grad.abs().max(), E2.grad.abs().max()
+    assert (h.grad.double() - h2.grad).abs().max() <= rtol * scale_h
+    assert (E.grad.double() - E2.grad).abs().max() <= rtol * scale_E
+    assert (h.grad[::3] == 0).all()                       # ignored rows get no gradient
+    assert torch.equal(pred.cpu(), (h2 @ E2.T).argmax(-1).cpu()) or dtype == torch.bfloat16
