@@ -43,8 +43,13 @@ def lm_head_loss_and_argmax(hidden_states: torch.Tensor, embedding_table: torch.
     fewer query rows with the reference's answer-only supervision."""
     dev = compute_device(hidden_states, embedding_table)
     B, T, D = hidden_states.shape
-    h = to_kernel_dtype(hidden_states.detach()).to(dev).reshape(B * T, D)
-    table = to_kernel_dtype(embedding_table.detach()).to(dev)
+    # training (run_training, multimodal_training.py:131-140): keep the autograd graph and route
+    # the loss through the differentiable wrapper; evaluation: plain fused scan
+    train = torch.is_grad_enabled() and labels is not None and (
+        hidden_states.requires_grad or embedding_table.requires_grad)
+    _d = (lambda t: t) if train else (lambda t: t.detach())
+    h = to_kernel_dtype(_d(hidden_states)).to(dev).reshape(B * T, D)
+    table = to_kernel_dtype(_d(embedding_table)).to(dev)
     if h.dtype != table.dtype:
         h = h.to(table.dtype)
     shifted = None
@@ -60,7 +65,14 @@ def lm_head_loss_and_argmax(hidden_states: torch.Tensor, embedding_table: torch.
         q, lab = h[sel], shifted[sel]
     pred = torch.full((B * T,), -1, dtype=torch.int64, device=dev)
     loss = None
-    if q.shape[0] > 0:
+    if q.shape[0] > 0 and train:
+        from ..autograd import fused_cross_entropy
+        loss, top1 = fused_cross_entropy(q, table, lab)
+        if sel is None:
+            pred = top1
+        else:
+            pred[sel] = top1
+    elif q.shape[0] > 0:
         out = ops.concept_scan(q, table, 1, normalize_q=False, normalize_t=False, labels=lab)
         if sel is None:
             pred = out.topk_idx[:, 0]

@@ -165,3 +165,26 @@ def test_f1_fused_cross_entropy_backward_matches_autograd(dtype, rtol, eps):
     assert (E.grad.double() - E2.grad).abs().max() <= rtol * scale_E
     assert (h.grad[::3] == 0).all()                       # ignored rows get no gradient
     assert torch.equal(pred.cpu(), (h2 @ E2.T).argmax(-1).cpu()) or dtype == torch.bfloat16
+
+
+def test_f1_lm_head_shim_trains_the_table():
+    """`language_embed_only` (mllm.py:181-184): the tied table receives gradients through the
+    shim exactly as through HF's logits + ForCausalLMLoss."""
+    from multimodal_concept_learning_b200.shims.mllm import lm_head_loss_and_argmax
+    g = torch.Generator().manual_seed(60)
+    B, T, D, V = 3, 9, 32, 700
+    hidden = (torch.randn(B, T, D, generator=g) * 0.3).cuda()
+    table = (torch.randn(V, D, generator=g) * 0.3).cuda().requires_grad_(True)
+    labels = torch.full((B, T), -100, dtype=torch.long)
+    labels[0, 5:7] = torch.tensor([3, 699])
+    labels[2, 8] = 41
+    out = lm_head_loss_and_argmax(hidden, table, labels.cuda())
+    out.loss.backward()
+    t2 = table.detach().double().requires_grad_(True)
+    want, _ = S.causal_lm_head_loss_ref(hidden.double().cpu(), t2.cpu(), labels, logits_dtype=torch.float64)
+    want.backward()
+    assert abs(float(out.loss.detach()) - float(want.detach())) <= 1e-4 * abs(float(want.detach()))
+    assert (table.grad.cpu().double() - t2.grad.cpu()).abs().max() <= 1e-4 * t2.grad.abs().max()
+    with torch.no_grad():
+        ev = lm_head_loss_and_argmax(hidden, table, labels.cuda())
+    assert not ev.loss.requires_grad
