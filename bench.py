@@ -148,6 +148,7 @@ def build_step(w, q, table, labels, lo, world, vocab_total):
         def step(qq=q):
             return sc.scan(qq, K_TOP, normalize_q=w["normalize"], scale=w["scale"], labels=labels,
                            inv_norm_q=inv_q if qq is q else None)
+        step.scanner, step.inv_t = sc, None
         return step, sc.close
     inv_t = mcl.row_inv_norm(table) if w["normalize"] else None   # cached per table version
     inv_q = mcl.row_inv_norm(q) if w["normalize"] else None
@@ -156,6 +157,7 @@ def build_step(w, q, table, labels, lo, world, vocab_total):
         return mcl.concept_scan(qq, table, K_TOP, normalize_q=w["normalize"], normalize_t=w["normalize"],
                                 scale=w["scale"], labels=labels, inv_norm_t=inv_t,
                                 inv_norm_q=inv_q if qq is q else None)
+    step.scanner, step.inv_t = None, inv_t
     return step, (lambda: None)
 
 
@@ -177,26 +179,22 @@ def run_workload(name, steps, warmup, world, rank, device, with_e2e=True, sample
     res["tflops"] = flops / (ms / steps * 1e-3) / 1e12
     res["alg_bytes"] = 2.0 * (w["V"] * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * K_TOP + 16)
     if with_e2e:
-        # same metric through the public API with HOST buffers: pinned q in, results out
+        # same metric through the public API with HOST buffers: every step copies the query batch
+        # from pinned host memory and returns (top-k values, indices, stats) in host memory.
+        # HostQueryPipeline overlaps the copies of neighbouring steps with the scan.
+        from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
         q_host = q.cpu().pin_memory()
-        q_dev = torch.empty_like(q)
+        pipe = HostQueryPipeline(table, K_TOP, normalize=w["normalize"], scale=w["scale"],
+                                 inv_norm_t=step.inv_t, scanner=step.scanner)
         outs = None
-
-        def e2e_step():
-            nonlocal outs
-            q_dev.copy_(q_host, non_blocking=True)
-            o = step(q_dev)
-            outs = (o.topk_val.to("cpu", non_blocking=True), o.topk_idx.to("cpu", non_blocking=True),
-                    o.stats.to("cpu", non_blocking=True))
-            torch.cuda.current_stream(device).synchronize()    # the caller reads the result
-        for _ in range(max(1, warmup // 2)):
-            e2e_step()
+        for outs in pipe.run((q_host for _ in range(max(2, warmup // 2))), labels):
+            pass
         torch.cuda.synchronize(device)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            e2e_step()
+        for outs in pipe.run((q_host for _ in range(steps)), labels):
+            pass                                           # the caller holds the result on the host
         torch.cuda.synchronize(device)
         dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
         if world > 1:

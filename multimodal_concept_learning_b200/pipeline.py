@@ -1,0 +1,84 @@
+"""Streaming front end for host-resident query batches: overlaps the host->device copy of batch
+i+1 and the device->host copy of result i-1 with the scan of batch i (two CUDA streams, two
+device buffers, events -- no host synchronisation inside the loop except on the result that is
+handed back).  This is the path a caller with queries in pinned host memory uses; `bench.py`
+measures its `e2e` number through it."""
+from __future__ import annotations
+
+from typing import Iterable, Iterator, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+class HostQueryPipeline:
+    def __init__(self, table: torch.Tensor, k: int, *, normalize: bool = True, scale: float = 1.0,
+                 inv_norm_t: Optional[torch.Tensor] = None, scanner=None):
+        if not table.is_cuda:
+            raise RuntimeError("table must be a CUDA tensor (no CPU fallback)")
+        self.table, self.k, self.normalize, self.scale = table, int(k), normalize, float(scale)
+        self.device = table.device
+        self.scanner = scanner            # an optional sharded.ShardedConceptScan
+        self.inv_norm_t = inv_norm_t
+        if normalize and inv_norm_t is None and scanner is None:
+            self.inv_norm_t = ops.row_inv_norm(table)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._bufs = [None, None]
+
+    def _scan(self, q: torch.Tensor, labels) -> ops.ScanOutput:
+        if self.scanner is not None:
+            return self.scanner.scan(q, self.k, normalize_q=self.normalize, scale=self.scale, labels=labels)
+        return ops.concept_scan(q, self.table, self.k, normalize_q=self.normalize,
+                                normalize_t=self.normalize, scale=self.scale, labels=labels,
+                                inv_norm_t=self.inv_norm_t)
+
+    def run(self, host_batches: Iterable[torch.Tensor], labels: Optional[torch.Tensor] = None
+            ) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        """Yields (topk_val, topk_idx, stats) as pinned HOST tensors, one per input batch, in
+        order.  Each host batch should be pinned for the copies to be asynchronous."""
+        main = torch.cuda.current_stream(self.device)
+        pending = None                    # (host results, event) of the previous batch
+        it = iter(host_batches)
+        nxt = next(it, None)
+        slot = 0
+        staged = None
+        if nxt is not None:
+            staged = self._stage(nxt, slot, main)
+        while staged is not None:
+            q_dev, ready = staged
+            nxt = next(it, None)
+            slot ^= 1
+            staged = self._stage(nxt, slot, main) if nxt is not None else None   # H2D of i+1
+            main.wait_event(ready)
+            out = self._scan(q_dev, labels)                                      # scan of i
+            done = torch.cuda.Event()
+            done.record(main)
+            self.copy_stream.wait_event(done)
+            with torch.cuda.stream(self.copy_stream):                            # D2H of i
+                host = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                             .copy_(t, non_blocking=True) for t in (out.topk_val, out.topk_idx, out.stats))
+                copied = torch.cuda.Event()
+                copied.record(self.copy_stream)
+            for t in (out.topk_val, out.topk_idx, out.stats):
+                t.record_stream(self.copy_stream)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (host, copied)
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+
+    def _stage(self, host_q: torch.Tensor, slot: int, main):
+        buf = self._bufs[slot]
+        if buf is None or buf.shape != host_q.shape or buf.dtype != host_q.dtype:
+            buf = torch.empty(host_q.shape, dtype=host_q.dtype, device=self.device)
+            self._bufs[slot] = buf
+        # the buffer may still be read by the scan two batches ago
+        self.copy_stream.wait_stream(main)
+        with torch.cuda.stream(self.copy_stream):
+            buf.copy_(host_q, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return buf, ev

@@ -188,3 +188,18 @@ def test_f1_lm_head_shim_trains_the_table():
     with torch.no_grad():
         ev = lm_head_loss_and_argmax(hidden, table, labels.cuda())
     assert not ev.loss.requires_grad
+
+
+def test_host_query_pipeline_matches_direct_scan():
+    import multimodal_concept_learning_b200 as mcl
+    from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
+    g = torch.Generator().manual_seed(70)
+    table = torch.randn(5000, 128, generator=g).to(torch.bfloat16).cuda()
+    batches = [torch.randn(200, 128, generator=g).to(torch.bfloat16).pin_memory() for _ in range(5)]
+    pipe = HostQueryPipeline(table, 20, scale=10.0)
+    got = list(pipe.run(batches))
+    assert len(got) == 5
+    for b, (val, idx, stats) in zip(batches, got):
+        ref = mcl.concept_scan(b.cuda(), table, 20, scale=10.0)
+        assert not val.is_cuda and torch.equal(val, ref.topk_val.cpu()) and torch.equal(idx, ref.topk_idx.cpu())
+        torch.testing.assert_close(stats, ref.stats.cpu(), rtol=1e-6, atol=1e-6)
