@@ -114,6 +114,21 @@ int mcl_concept_scan(const void* q /*[Q,D]*/, const void* table /*[V_local,D]*/,
                      float* row_stats /*[Q,4]*/, void* workspace, size_t workspace_bytes,
                      mcl_stream_t stream);
 
+/*
+ * Soft-capped variant: every logit is z' = softcap * tanh(z / softcap) before the top-k values,
+ * the log-sum-exp, sum_z and z_label are formed (ranking is by z: tanh is monotone).
+ * softcap = 0 is mcl_concept_scan.  scores_out is nullable (a [Q,V_local] dump of z' for tests).
+ * Replaces: the `final_logit_softcapping` branch of the HF LM head that mllm.py:115 reaches,
+ *   site-packages/transformers/models/gemma3/modeling_gemma3.py:653-656 (None for Gemma-3-1B,
+ *   30.0 for the Gemma-2-2B of random_experiments/multi_token_embedding).
+ */
+int mcl_concept_scan_softcap(const void* q, const void* table, int dtype, int64_t Q,
+                             int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                             const float* inv_norm_q, const float* inv_norm_t, float scale,
+                             float softcap, int k, int64_t index_base, const int64_t* labels,
+                             float* topk_val, int64_t* topk_idx, float* row_stats, void* workspace,
+                             size_t workspace_bytes, float* scores_out, mcl_stream_t stream);
+
 /* Same call, additionally dumping z to scores_out [Q, V_local] fp32 (tests only). */
 int mcl_concept_scan_debug(const void* q, const void* table, int dtype, int64_t Q,
                            int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,

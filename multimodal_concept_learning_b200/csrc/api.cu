@@ -109,10 +109,11 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
               int64_t ldq, int64_t ldt, const float* inv_q, const float* inv_t, float scale, int k,
               int64_t index_base, const int64_t* labels, float* topk_val, int64_t* topk_idx,
               float* row_stats, void* workspace, size_t workspace_bytes, float* dbg,
-              cudaStream_t stream) {
+              cudaStream_t stream, float softcap = 0.f) {
   int rc = check_scan_args(q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, topk_val,
                            topk_idx, row_stats);
   if (rc) return rc;
+  if (!(softcap >= 0.f) || !(softcap < INFINITY)) return fail(MCL_ERR_BAD_ARG, "softcap must be finite and >= 0");
   DevInfo di;
   if ((rc = require_sm100(&di))) return rc;
   if (Q == 0) return MCL_OK;
@@ -127,7 +128,7 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
-             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr};
+             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap};
   int merge_split = 1;
   cudaError_t e;
   if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
@@ -143,7 +144,7 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
     merge_split = nsplit;
   }
   g_launches++;
-  e = launch_merge_slots(ws.sv, merge_split, Q, k, inv_q, scale, index_base, topk_val, topk_idx, row_stats, stream);
+  e = launch_merge_slots(ws.sv, merge_split, Q, k, inv_q, scale, softcap, index_base, topk_val, topk_idx, row_stats, stream);
   if (e != cudaSuccess) return cuda_fail(e, "merge launch");
   g_launches++;
   return MCL_OK;
@@ -272,6 +273,17 @@ int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int
   return scan_impl(q, table, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, k,
                    index_base, labels, topk_val, topk_idx, row_stats, workspace, workspace_bytes,
                    nullptr, (cudaStream_t)stream);
+}
+
+int mcl_concept_scan_softcap(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
+                             int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                             const float* inv_norm_t, float scale, float softcap, int k,
+                             int64_t index_base, const int64_t* labels, float* topk_val,
+                             int64_t* topk_idx, float* row_stats, void* workspace,
+                             size_t workspace_bytes, float* scores_out, mcl_stream_t stream) {
+  return scan_impl(q, table, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, k,
+                   index_base, labels, topk_val, topk_idx, row_stats, workspace, workspace_bytes,
+                   scores_out, (cudaStream_t)stream, softcap);
 }
 
 int mcl_concept_scan_debug(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,

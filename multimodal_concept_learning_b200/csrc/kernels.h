@@ -21,6 +21,7 @@ struct ScanArgs {
   void* timing;              // nullable, [grid][2] uint64 (tcgen05 scan only)
   void* tau_shared;          // nullable, [num_rb*128] uint32 zeroed before launch (tcgen05 scan)
   void* sync_ctr;            // [rounds*ng*nwin] int zeroed before launch (tcgen05 scan)
+  float softcap;             // 0 = off; c > 0: logits are c*tanh(z/c)
 };
 
 // Tile schedule of the tcgen05 scan (see scan_tc.cu): ng groups of g CTAs; in round r member m
@@ -52,7 +53,7 @@ cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, 
 
 // slots -> final [Q,k] / [Q,4]
 cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
-                               const float* inv_q, float scale, int64_t index_base,
+                               const float* inv_q, float scale, float softcap, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s);
 // R per-shard results (rank r's arrays start r * stride bytes after the base) -> final

@@ -80,7 +80,7 @@ constexpr int kPendCap = 96;
 template <int kMergeWarps>
 __global__ void __launch_bounds__(32 * kMergeWarps)
 merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restrict__ inv_q,
-                   float scale, long long index_base, float* __restrict__ topk_val,
+                   float scale, float softcap, long long index_base, float* __restrict__ topk_val,
                    long long* __restrict__ topk_idx, float4* __restrict__ row_stats) {
   __shared__ unsigned long long pend[kMergeWarps][kPendCap];
   __shared__ unsigned long long lists[kMergeWarps][64];
@@ -137,7 +137,12 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
       unsigned long long key = 0ull;
       // rank by the OUTPUT value z = y * rs (what callers and the rank merge see), so that
       // scores whose z round to the same float tie-break by table row everywhere
-      if (j < n) { const uint2 e = b[j]; key = pack_key(__uint_as_float(e.x) * rs, e.y); }
+      if (j < n) {
+        const uint2 e = b[j];
+        float z = __uint_as_float(e.x) * rs;
+        if (softcap > 0.f) z = softcap * tanhf(z / softcap);
+        key = pack_key(z, e.y);
+      }
       const bool keep = key > kth;        // keys are unique, so > loses nothing
       const unsigned km = __ballot_sync(0xffffffffu, keep);
       if (keep) q[npend + __popc(km & lt)] = key;
@@ -229,18 +234,18 @@ merge_ranks_kernel(const char* __restrict__ val_b, const char* __restrict__ idx_
 }
 
 cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
-                               const float* inv_q, float scale, int64_t index_base,
+                               const float* inv_q, float scale, float softcap, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s) {
   if (Q == 0) return cudaSuccess;
   // few rows with many slots (small Q split over all SMs): more warps per row
   if (nsplit > 32 && Q <= 4096)
     merge_slots_kernel<16><<<(unsigned)Q, 32 * 16, 0, s>>>(
-        sv, nsplit, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
+        sv, nsplit, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   else
     merge_slots_kernel<4><<<(unsigned)Q, 32 * 4, 0, s>>>(
-        sv, nsplit, (int)Q, k, inv_q, scale, (long long)index_base, topk_val, (long long*)topk_idx,
+        sv, nsplit, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   return cudaGetLastError();
 }

@@ -52,9 +52,12 @@ struct RowState {
 
 // One chunk of 32 scores for this thread's row.  col0 = local table row of y[0];
 // n_valid < 32 only in the ragged last chunk (TAIL), whose out-of-range columns are masked.
-template <bool TAIL>
+// CAP: tanh soft-capped logits z' = c*tanh(z/c) (Gemma-2 style heads, modeling_gemma3.py:653-656):
+// rc = rs/c, `a` = c*log2(e); max / sum-exp / sum run on t = tanh(y*rc), ranking stays on y
+// (tanh is monotone), and row_flush scales by c.
+template <bool TAIL, bool CAP>
 __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChunk], int col0,
-                                                  int n_valid, float a, int lab_local) {
+                                                  int n_valid, float a, int lab_local, float rc) {
   if (TAIL) {
 #pragma unroll
     for (int i = 0; i < kChunk; ++i)
@@ -74,15 +77,29 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
 
   // online log-sum-exp in base 2
   const float m_new = fmaxf(st.m, cm);
-  const float corr = ex2_fast((st.m - m_new) * a);  // first chunk: exp2(-inf) = 0, s is 0 anyway
-  const float mb = m_new * a;
   float acc = 0.f, sy = 0.f;
+  if (!CAP) {
+    const float corr = ex2_fast((st.m - m_new) * a);  // first chunk: exp2(-inf) = 0, s is 0 anyway
+    const float mb = m_new * a;
 #pragma unroll
-  for (int i = 0; i < kChunk; ++i) {
-    acc += ex2_fast(fmaf(y[i], a, -mb));            // masked columns: exp2(-inf) = 0
-    if (TAIL) sy += (i < n_valid) ? y[i] : 0.f; else sy += y[i];
+    for (int i = 0; i < kChunk; ++i) {
+      acc += ex2_fast(fmaf(y[i], a, -mb));            // masked columns: exp2(-inf) = 0
+      if (TAIL) sy += (i < n_valid) ? y[i] : 0.f; else sy += y[i];
+    }
+    st.s = fmaf(st.s, corr, acc);
+  } else {
+    const float mt_new = tanhf(m_new * rc);
+    const float corr = ex2_fast((tanhf(st.m * rc) - mt_new) * a);   // first chunk: s is 0
+    const float mb = mt_new * a;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const float t = tanhf(y[i] * rc);
+      const float e = ex2_fast(fmaf(t, a, -mb));
+      if (TAIL) { acc += (i < n_valid) ? e : 0.f; sy += (i < n_valid) ? t : 0.f; }
+      else { acc += e; sy += t; }
+    }
+    st.s = fmaf(st.s, corr, acc);
   }
-  st.s = fmaf(st.s, corr, acc);
   st.m = m_new;
   st.sum_y += sy;
 
@@ -221,10 +238,17 @@ __device__ __forceinline__ void row_apply_shared_tau(RowState& st, uint32_t shar
 }
 
 // Close a slot: candidate count and (m, s, sum_z, z_label) in z space for this row.
-__device__ __forceinline__ void row_flush(const RowState& st, float rs, int* cnt_out,
+// softcap c > 0: z' = c*tanh(z/c); sum_y already holds the sum of tanh values.
+__device__ __forceinline__ void row_flush(const RowState& st, float rs, float softcap, int* cnt_out,
                                           float4* stats_out) {
   *cnt_out = st.cnt;
-  *stats_out = make_float4(st.m * rs, st.s, st.sum_y * rs, st.y_label * rs);
+  if (softcap > 0.f) {
+    const float rc = rs / softcap;
+    *stats_out = make_float4(softcap * tanhf(st.m * rc), st.s, softcap * st.sum_y,
+                             softcap * tanhf(st.y_label * rc));
+  } else {
+    *stats_out = make_float4(st.m * rs, st.s, st.sum_y * rs, st.y_label * rs);
+  }
 }
 
 }  // namespace mcl

@@ -22,7 +22,7 @@ scan_simt_kernel(const T* __restrict__ q, const T* __restrict__ table, int Q, in
                  long long ldq, long long ldt, const float* __restrict__ inv_q,
                  const float* __restrict__ inv_t, float scale, int k, long long index_base,
                  const long long* __restrict__ labels, SlotView sv, int nsplit,
-                 int chunks_per_split, float* __restrict__ dbg_scores) {
+                 int chunks_per_split, float* __restrict__ dbg_scores, float softcap) {
   __shared__ float qs[kSimtK][kBlockM + 1];           // transposed query slice
   __shared__ __align__(16) float ts[kChunk][kSimtK + 4];  // table slice, row = table row
 
@@ -41,7 +41,8 @@ scan_simt_kernel(const T* __restrict__ q, const T* __restrict__ table, int Q, in
   uint2* warp_buf = slot_buf + (size_t)(warp * 32) * kCandCap;
 
   const float rs = (row < Q && inv_q ? inv_q[row] : 1.f) * scale;
-  const float a = rs * kLog2e;
+  const float a = (softcap > 0.f ? softcap : rs) * kLog2e;
+  const float rc = softcap > 0.f ? rs / softcap : 0.f;
   int lab_local = -1;
   if (labels && row < Q) {
     const long long l = labels[row] - index_base;
@@ -96,14 +97,21 @@ scan_simt_kernel(const T* __restrict__ q, const T* __restrict__ table, int Q, in
     if (dbg_scores && row < Q) {
 #pragma unroll
       for (int i = 0; i < kChunk; ++i)
-        if (i < n_valid) dbg_scores[(size_t)row * V + col0 + i] = acc[i] * rs;
+        if (i < n_valid)
+          dbg_scores[(size_t)row * V + col0 + i] =
+              softcap > 0.f ? softcap * tanhf(acc[i] * rc) : acc[i] * rs;
     }
-    if (n_valid == kChunk) row_process_chunk<false>(st, acc, col0, kChunk, a, lab_local);
-    else row_process_chunk<true>(st, acc, col0, n_valid, a, lab_local);
+    if (softcap > 0.f) {
+      if (n_valid == kChunk) row_process_chunk<false, true>(st, acc, col0, kChunk, a, lab_local, rc);
+      else row_process_chunk<true, true>(st, acc, col0, n_valid, a, lab_local, rc);
+    } else {
+      if (n_valid == kChunk) row_process_chunk<false, false>(st, acc, col0, kChunk, a, lab_local, 0.f);
+      else row_process_chunk<true, false>(st, acc, col0, n_valid, a, lab_local, 0.f);
+    }
     __syncwarp();
     warp_compact_rows(st, k, warp_buf, lane, nullptr);
   }
-  row_flush(st, rs, sv.cnt + (size_t)slot * kBlockM + tid, sv.stats + (size_t)slot * kBlockM + tid);
+  row_flush(st, rs, softcap, sv.cnt + (size_t)slot * kBlockM + tid, sv.stats + (size_t)slot * kBlockM + tid);
 }
 
 cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, cudaStream_t s) {
@@ -115,12 +123,12 @@ cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, 
     scan_simt_kernel<float><<<grid, kBlockM, 0, s>>>(
         (const float*)a.q, (const float*)a.table, (int)a.Q, (int)a.V, (int)a.D, a.ldq, a.ldt,
         a.inv_q, a.inv_t, a.scale, a.k, a.index_base, (const long long*)a.labels, sv, nsplit, cps,
-        a.dbg_scores);
+        a.dbg_scores, a.softcap);
   } else {
     scan_simt_kernel<__nv_bfloat16><<<grid, kBlockM, 0, s>>>(
         (const __nv_bfloat16*)a.q, (const __nv_bfloat16*)a.table, (int)a.Q, (int)a.V, (int)a.D,
         a.ldq, a.ldt, a.inv_q, a.inv_t, a.scale, a.k, a.index_base, (const long long*)a.labels, sv,
-        nsplit, cps, a.dbg_scores);
+        nsplit, cps, a.dbg_scores, a.softcap);
   }
   return cudaGetLastError();
 }

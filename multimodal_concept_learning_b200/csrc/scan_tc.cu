@@ -55,6 +55,7 @@ struct TcParams {
   uint32_t* tau_shared;         // [num_rb*128] order-preserving keys, zeroed before the launch
   int* sync_ctr;                // [rounds][ng][nwin] members that started a window, zeroed
   int win, nwin;
+  float softcap;                // 0 = off; c > 0: logits are c*tanh(z/c) (kCap instantiation)
 };
 
 // kCS = CTAs per cluster.  kCS = 1: every CTA multiplies its own 128 x 256 tile
@@ -66,7 +67,7 @@ struct TcParams {
 // traffic (TMA writes + MMA reads) by a third -- the single-CTA tile is bound by it -- and each
 // CTA still finds its own 128 rows x 256 columns of accumulators in its own TMEM, so the
 // epilogue is identical.
-template <int kCS>
+template <int kCS, bool kCap>
 __global__ void __launch_bounds__(kTcThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_t,
                const TcParams p) {
@@ -137,8 +138,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const int w = (vt - vt0) / p.win;
             atomicAdd(ctr + w, 1);
             if (w >= 2) {
+              // bounded (~1 s): if a co-resident peer never shows up (SMs held by foreign work)
+              // give up the L2 locality rather than hang
               const volatile int* c = ctr + (w - 2);
-              while (*c < members) __nanosleep(256);
+              for (int spin = 0; *c < members && spin < (1 << 22); ++spin) __nanosleep(256);
             }
           }
           for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -229,7 +232,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       row = (long long)rb * kBlockM + row_in_tile;
       if (row >= p.Q) st.tau = INFINITY;                // padding rows never append / compact
       rs = ((row < p.Q && p.inv_q) ? p.inv_q[row] : 1.f) * p.scale;
-      a = rs * kLog2e;
+      a = (kCap ? p.softcap : rs) * kLog2e;
+      const float rc = kCap ? rs / p.softcap : 0.f;
       lab_local = -1;
       if (p.labels && row < p.Q) {
         const long long lg = p.labels[row];
@@ -282,10 +286,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           if (p.dbg_scores && row < p.Q) {
 #pragma unroll
             for (int i = 0; i < kChunk; ++i)
-              if (i < n_valid) p.dbg_scores[(size_t)row * p.V + col0 + i] = y[i] * rs;
+              if (i < n_valid)
+                p.dbg_scores[(size_t)row * p.V + col0 + i] =
+                    kCap ? p.softcap * tanhf(y[i] * rc) : y[i] * rs;
           }
-          if (n_valid == kChunk) row_process_chunk<false>(st, y, col0, kChunk, a, lab_local);
-          else row_process_chunk<true>(st, y, col0, n_valid, a, lab_local);
+          if (n_valid == kChunk) row_process_chunk<false, kCap>(st, y, col0, kChunk, a, lab_local, rc);
+          else row_process_chunk<true, kCap>(st, y, col0, n_valid, a, lab_local, rc);
           __syncwarp();
           warp_compact_rows(st, p.k, warp_buf, lane, tau_pub);
         };
@@ -305,7 +311,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         acc ^= 1u; if (acc == 0) acc_phase ^= 1u;
         tb ^= 1u;
       }
-      row_flush(st, rs, p.sv.cnt + (size_t)slot * kBlockM + row_in_tile,
+      row_flush(st, rs, kCap ? p.softcap : 0.f, p.sv.cnt + (size_t)slot * kBlockM + row_in_tile,
                 p.sv.stats + (size_t)slot * kBlockM + row_in_tile);
     }
   }
@@ -442,11 +448,12 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev].load()) {
-    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kTcSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)kTcSmemBytes);
+    cudaError_t e = cudaSuccess;
+    const void* kernels[4] = {(const void*)scan_tc_kernel<1, false>, (const void*)scan_tc_kernel<2, false>,
+                              (const void*)scan_tc_kernel<1, true>, (const void*)scan_tc_kernel<2, true>};
+    for (const void* kfn : kernels)
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(smem=%u)", kTcSmemBytes); return e; }
     attr_set[dev].store(true);
   }
@@ -467,6 +474,8 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   p.sv = sv; p.dbg_scores = a.dbg_scores; p.timing = (unsigned long long*)a.timing;
   p.tau_shared = (uint32_t*)a.tau_shared;
   p.sync_ctr = (int*)a.sync_ctr; p.win = sch.win; p.nwin = sch.nwin;
+  p.softcap = a.softcap;
+  const bool cap = a.softcap > 0.f;
   // Cooperative launch: the drift bound makes CTAs wait for one another, so all of them must
   // be resident at once (grid <= SM count, one CTA per SM); the runtime checks exactly that.
   cudaLaunchConfig_t cfg{};
@@ -483,10 +492,12 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   if (cs == 2) {   // clusters: co-residency follows from grid <= SM count with one CTA per SM
     cfg.attrs = attr + 1;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, scan_tc_kernel<2>, tm_q, tm_t, p);
+    return cap ? cudaLaunchKernelEx(&cfg, scan_tc_kernel<2, true>, tm_q, tm_t, p)
+               : cudaLaunchKernelEx(&cfg, scan_tc_kernel<2, false>, tm_q, tm_t, p);
   }
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, scan_tc_kernel<1>, tm_q, tm_t, p);
+  return cap ? cudaLaunchKernelEx(&cfg, scan_tc_kernel<1, true>, tm_q, tm_t, p)
+             : cudaLaunchKernelEx(&cfg, scan_tc_kernel<1, false>, tm_q, tm_t, p);
 }
 
 }  // namespace mcl

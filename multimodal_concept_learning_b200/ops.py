@@ -111,7 +111,7 @@ def _(table, offsets, ids, normalize):
 @torch.library.custom_op("mcl::concept_scan", mutates_args=(), device_types="cuda")
 def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
                      inv_norm_t: Optional[Tensor], labels: Optional[Tensor], scale: float,
-                     k: int, index_base: int) -> Tuple[Tensor, Tensor, Tensor]:
+                     k: int, index_base: int, softcap: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
     lib = load()
     dev = q.device
     Q, D = q.shape
@@ -123,16 +123,24 @@ def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
     with torch.cuda.device(dev):
         ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.mcl_concept_scan(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
-                                   table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t),
-                                   float(scale), k, index_base, _ptr(labels), val.data_ptr(),
-                                   idx.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes,
-                                   _stream(dev)))
+        if softcap > 0.0:
+            check(lib.mcl_concept_scan_softcap(q.data_ptr(), table.data_ptr(), code, Q, V, D,
+                                               q.stride(0), table.stride(0), _ptr(inv_norm_q),
+                                               _ptr(inv_norm_t), float(scale), float(softcap), k,
+                                               index_base, _ptr(labels), val.data_ptr(),
+                                               idx.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                                               ws_bytes, None, _stream(dev)))
+        else:
+            check(lib.mcl_concept_scan(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
+                                       table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t),
+                                       float(scale), k, index_base, _ptr(labels), val.data_ptr(),
+                                       idx.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes,
+                                       _stream(dev)))
     return val, idx, stats
 
 
 @_concept_scan_op.register_fake
-def _(q, table, inv_norm_q, inv_norm_t, labels, scale, k, index_base):
+def _(q, table, inv_norm_q, inv_norm_t, labels, scale, k, index_base, softcap=0.0):
     Q = q.shape[0]
     return (q.new_empty((Q, k), dtype=torch.float32), q.new_empty((Q, k), dtype=torch.int64),
             q.new_empty((Q, 4), dtype=torch.float32))
@@ -214,11 +222,12 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
                  normalize_t: bool = True, scale: float = 1.0, labels: Optional[Tensor] = None,
                  label_smoothing: float = 0.0, inv_norm_q: Optional[Tensor] = None,
                  inv_norm_t: Optional[Tensor] = None, index_base: int = 0,
-                 vocab_total: Optional[int] = None) -> ScanOutput:
+                 vocab_total: Optional[int] = None, softcap: Optional[float] = None) -> ScanOutput:
     """Fused similarity scan of ``q [Q,D]`` against ``table [V,D]``: row-wise top-k and the
     log-sum-exp / cross-entropy statistics, without materialising the [Q,V] scores.
     ``normalize_*`` select cosine (True) vs raw dot product (False); a cached
-    ``inv_norm_t`` (from :func:`row_inv_norm`) avoids re-reading the table."""
+    ``inv_norm_t`` (from :func:`row_inv_norm`) avoids re-reading the table.  ``softcap=c`` applies
+    Gemma-2 style ``c * tanh(z / c)`` to every logit (HF ``final_logit_softcapping``)."""
     dev = _require_cuda(q, table, inv_norm_q, inv_norm_t)      # labels may arrive on the host
     if q.dtype != table.dtype:
         raise TypeError(f"q ({q.dtype}) and table ({table.dtype}) must have the same dtype")
@@ -244,15 +253,18 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
         labels = labels.to(device=dev, dtype=torch.int64).contiguous()
         if labels.shape != (q.shape[0],):
             raise ValueError(f"labels must have shape [{q.shape[0]}]")
+    if softcap is not None and not softcap > 0:
+        raise ValueError("softcap must be > 0 (or None)")
     val, idx, stats = torch.ops.mcl.concept_scan(q, table, inv_norm_q, inv_norm_t, labels,
-                                                 float(scale), int(k), int(index_base))
+                                                 float(scale), int(k), int(index_base),
+                                                 float(softcap or 0.0))
     return ScanOutput(val, idx, stats, int(vocab_total or table.shape[0]), labels,
                       float(label_smoothing))
 
 
 def concept_scan_debug(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv_norm_t=None,
                        scale: float = 1.0, labels=None, index_base: int = 0,
-                       label_smoothing: float = 0.0):
+                       label_smoothing: float = 0.0, softcap: float = 0.0):
     """Test hook: the same kernels, additionally dumping the score matrix [Q,V]."""
     lib = load()
     dev = _require_cuda(q, table)
@@ -269,12 +281,12 @@ def concept_scan_debug(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None, inv
     with torch.cuda.device(dev):
         ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.mcl_concept_scan_debug(q.data_ptr(), table.data_ptr(), code, Q, V, D,
-                                         q.stride(0), table.stride(0), _ptr(inv_norm_q),
-                                         _ptr(inv_norm_t), float(scale), k, index_base,
-                                         _ptr(labels), val.data_ptr(), idx.data_ptr(),
-                                         stats.data_ptr(), ws.data_ptr(), ws_bytes,
-                                         scores.data_ptr(), _stream(dev)))
+        check(lib.mcl_concept_scan_softcap(q.data_ptr(), table.data_ptr(), code, Q, V, D,
+                                           q.stride(0), table.stride(0), _ptr(inv_norm_q),
+                                           _ptr(inv_norm_t), float(scale), float(softcap), k,
+                                           index_base, _ptr(labels), val.data_ptr(), idx.data_ptr(),
+                                           stats.data_ptr(), ws.data_ptr(), ws_bytes,
+                                           scores.data_ptr(), _stream(dev)))
     return ScanOutput(val, idx, stats, V, labels, float(label_smoothing)), scores
 
 

@@ -61,7 +61,7 @@ class ScanResult:
 
 
 def scores_ref(q, table, *, normalize_q=True, normalize_t=True, scale=1.0,
-               dtype=torch.float64) -> torch.Tensor:
+               dtype=torch.float64, softcap=None) -> torch.Tensor:
     qf = q.detach().to("cpu").to(dtype)
     tf = table.detach().to("cpu").to(dtype)
     z = qf @ tf.T
@@ -69,7 +69,10 @@ def scores_ref(q, table, *, normalize_q=True, normalize_t=True, scale=1.0,
         z = z * row_inv_norm_ref(q, dtype)[:, None]
     if normalize_t:
         z = z * row_inv_norm_ref(table, dtype)[None, :]
-    return z * scale
+    z = z * scale
+    if softcap:   # modeling_gemma3.py:653-656: logits / c -> tanh -> * c
+        z = torch.tanh(z / softcap) * softcap
+    return z
 
 
 def topk_lowest_index(z: torch.Tensor, k: int):
@@ -106,12 +109,12 @@ def loss_from_stats(lse, sum_z, z_label, labels, vocab: int, label_smoothing: fl
 def concept_scan_ref(q, table, k: int, *, normalize_q=True, normalize_t=True, scale=1.0,
                      labels: Optional[torch.Tensor] = None, label_smoothing: float = 0.0,
                      index_base: int = 0, vocab_total: Optional[int] = None,
-                     dtype=torch.float64, keep_scores=False) -> ScanResult:
+                     dtype=torch.float64, keep_scores=False, softcap=None) -> ScanResult:
     """The whole path on CPU.  ``dtype=float64`` is the ground truth on the given
     (possibly bf16) input values; ``float32`` is what the reference's own fp32
     composition computes."""
     z = scores_ref(q, table, normalize_q=normalize_q, normalize_t=normalize_t, scale=scale,
-                   dtype=dtype)
+                   dtype=dtype, softcap=softcap)
     V = z.shape[1]
     if not 1 <= k <= V:
         raise ValueError(f"k={k} out of range for V={V}")

@@ -273,3 +273,26 @@ def test_full_size_properties_qwen2vl_scale(mcl):
     z = torch.nn.functional.normalize(q[sub].float(), dim=1) @ torch.nn.functional.normalize(t.float(), dim=1).T
     check_topk(full.topk_val[sub], full.topk_idx[sub], z, k, rtol=RTOL, atol=1e-5)
     torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4)
+
+
+# ---- soft-capped logits ----------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_softcap_logits(mcl, dtype):
+    """c*tanh(z/c) on every logit (HF final_logit_softcapping): top-k values, LSE, CE."""
+    q, t = make_inputs(150, 3000, 128, 90, dtype=dtype)
+    q, t = (q.float() * 0.6).to(dtype), (t.float() * 0.6).to(dtype)      # |z| up to ~20 vs cap 8
+    labels = torch.randint(0, 3000, (150,), generator=torch.Generator().manual_seed(90))
+    labels[::4] = -100
+    cap = 8.0
+    ref = R.concept_scan_ref(q, t, 20, normalize_q=False, normalize_t=False, labels=labels,
+                             label_smoothing=0.1, softcap=cap, keep_scores=True)
+    out, scores = mcl.concept_scan_debug(q.cuda(), t.cuda(), 20, labels=labels, label_smoothing=0.1,
+                                         softcap=cap)
+    torch.testing.assert_close(scores.cpu().double(), ref.scores, rtol=RTOL, atol=1e-4)
+    check_topk(out.topk_val, out.topk_idx, ref.scores, 20, rtol=RTOL, atol=1e-4)
+    check_stats(out.stats, ref, rtol=RTOL, atol=1e-3)
+    torch.testing.assert_close(out.loss.cpu().double(), ref.loss.double(), rtol=RTOL, atol=1e-5)
+    plain = mcl.concept_scan(q.cuda(), t.cuda(), 20, normalize_q=False, normalize_t=False,
+                             labels=labels, softcap=cap)
+    assert torch.equal(plain.topk_idx, out.topk_idx) and torch.equal(plain.topk_val, out.topk_val)
+    assert float(out.topk_val.max()) < cap
