@@ -16,7 +16,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0};
+std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -157,6 +157,8 @@ typedef int (*nccl_init_rank_t)(void**, int, NcclUid, int);
 typedef int (*nccl_destroy_t)(void*);
 typedef int (*nccl_allgather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*nccl_errstr_t)(int);
+typedef int (*nccl_sendrecv_t)(void*, size_t, int, int, void*, cudaStream_t);   // send (const void*) / recv
+typedef int (*nccl_group_t)(void);
 struct NcclApi {
   void* h = nullptr;
   nccl_get_uid_t get_uid = nullptr;
@@ -164,6 +166,8 @@ struct NcclApi {
   nccl_destroy_t destroy = nullptr;
   nccl_allgather_t allgather = nullptr;
   nccl_errstr_t errstr = nullptr;
+  nccl_sendrecv_t send = nullptr, recv = nullptr;
+  nccl_group_t group_start = nullptr, group_end = nullptr;
 };
 NcclApi* nccl() {
   static NcclApi api;
@@ -180,6 +184,10 @@ NcclApi* nccl() {
     api.destroy = (nccl_destroy_t)dlsym(api.h, "ncclCommDestroy");
     api.allgather = (nccl_allgather_t)dlsym(api.h, "ncclAllGather");
     api.errstr = (nccl_errstr_t)dlsym(api.h, "ncclGetErrorString");
+    api.send = (nccl_sendrecv_t)dlsym(api.h, "ncclSend");
+    api.recv = (nccl_sendrecv_t)dlsym(api.h, "ncclRecv");
+    api.group_start = (nccl_group_t)dlsym(api.h, "ncclGroupStart");
+    api.group_end = (nccl_group_t)dlsym(api.h, "ncclGroupEnd");
   });
   if (!api.h || !api.get_uid || !api.init_rank || !api.destroy || !api.allgather) return nullptr;
   return &api;
@@ -366,7 +374,9 @@ int mcl_comm_destroy(void* comm) {
 
 size_t mcl_sharded_gather_bytes(int64_t Q, int k, int world) {
   if (Q < 0 || k < 1 || world < 1) return 0;
-  return record_layout(Q, k).bytes * (size_t)world;
+  // R full records (all-gather path) + room for R mini-records of Q/R rows (row-exchange path)
+  const size_t rec = record_layout(Q, k).bytes;
+  return rec * (size_t)world + rec + (size_t)world * 1024;
 }
 
 int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, int64_t Q,
@@ -378,9 +388,10 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
                              void* comm, int world, int rank, mcl_stream_t stream) {
   if (world < 1 || rank < 0 || rank >= world) return fail(MCL_ERR_BAD_ARG, "bad world/rank");
   const Record rec = record_layout(Q, k);
-  if (!gather_buf || gather_bytes < rec.bytes * (size_t)world || !aligned16(gather_buf))
+  const size_t gather_need = mcl_sharded_gather_bytes(Q, k, world);
+  if (!gather_buf || gather_bytes < gather_need || !aligned16(gather_buf))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "gather_buf %zu B < required %zu B", gather_bytes,
-                rec.bytes * (size_t)world);
+                gather_need);
   char* mine = (char*)gather_buf + rec.bytes * (size_t)rank;
   // 1. local scan straight into this rank's record of the gather buffer
   int rc = scan_impl(q, table_shard, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale,
@@ -388,23 +399,71 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
                      (int64_t*)(mine + rec.idx_off), (float*)(mine + rec.stats_off), workspace,
                      workspace_bytes, nullptr, (cudaStream_t)stream);
   if (rc) return rc;
-  // 2. one all-gather of the packed records (in place)
+  NcclApi* n = nullptr;
   if (world > 1) {
-    NcclApi* n = nccl();
+    n = nccl();
     if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable");
     if (!comm) return fail(MCL_ERR_BAD_ARG, "null communicator");
-    int nrc = n->allgather(mine, gather_buf, rec.bytes, /*ncclInt8*/ 0, comm, (cudaStream_t)stream);
-    if (nrc) return nccl_fail(n, nrc, "ncclAllGather");
   }
-  // 3. merge the R records
   char* base = (char*)gather_buf;
-  cudaError_t e = launch_merge_ranks((const float*)(base + rec.val_off),
-                                     (const int64_t*)(base + rec.idx_off),
-                                     (const float*)(base + rec.stats_off), rec.bytes, rec.bytes,
-                                     rec.bytes, world, Q, k, topk_val, topk_idx, row_stats,
+  const bool exchange = world > 2 && Q % world == 0 && n->send && n->recv && n->group_start &&
+                        n->group_end && !g_opt_allgather.load();
+  if (!exchange) {
+    // 2a. one all-gather of the packed records (in place), 3a. every rank merges all Q rows
+    if (world > 1) {
+      int nrc = n->allgather(mine, gather_buf, rec.bytes, /*ncclInt8*/ 0, comm, (cudaStream_t)stream);
+      if (nrc) return nccl_fail(n, nrc, "ncclAllGather");
+    }
+    cudaError_t e = launch_merge_ranks((const float*)(base + rec.val_off),
+                                       (const int64_t*)(base + rec.idx_off),
+                                       (const float*)(base + rec.stats_off), rec.bytes, rec.bytes,
+                                       rec.bytes, world, Q, k, topk_val, topk_idx, row_stats,
+                                       (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "merge launch");
+    if (Q) g_launches++;
+    return MCL_OK;
+  }
+  // 2b. Larger worlds: rank j merges only query rows [j*Q/N, (j+1)*Q/N).  Every rank sends each
+  // peer that peer's row range of its local lists (one grouped send/recv exchange, 1/N of the
+  // all-gather's bytes), merges its own rows, and the merged rows are all-gathered straight into
+  // the output arrays.  The local record sits in slot `rank` of gather_buf; the R mini-records
+  // of Q/N rows are received behind the R full slots.
+  const int64_t rows = Q / world;
+  const Record mini = record_layout(rows, k);
+  char* area = base + rec.bytes * (size_t)world;          // receive area behind the R records
+  const size_t vb = (size_t)rows * k * 4, ib = (size_t)rows * k * 8, sb = (size_t)rows * 16;
+  int nrc = n->group_start();
+  if (nrc) return nccl_fail(n, nrc, "ncclGroupStart");
+  for (int peer = 0; peer < world; ++peer) {
+    char* dst = area + mini.bytes * (size_t)peer;          // rows of MINE as computed by `peer`
+    const size_t r0 = (size_t)peer * rows;                  // rows of PEER as computed by me
+    if (!nrc) nrc = n->send(mine + rec.val_off + r0 * k * 4, vb, 0, peer, comm, (cudaStream_t)stream);
+    if (!nrc) nrc = n->send(mine + rec.idx_off + r0 * k * 8, ib, 0, peer, comm, (cudaStream_t)stream);
+    if (!nrc) nrc = n->send(mine + rec.stats_off + r0 * 16, sb, 0, peer, comm, (cudaStream_t)stream);
+    if (!nrc) nrc = n->recv(dst + mini.val_off, vb, 0, peer, comm, (cudaStream_t)stream);
+    if (!nrc) nrc = n->recv(dst + mini.idx_off, ib, 0, peer, comm, (cudaStream_t)stream);
+    if (!nrc) nrc = n->recv(dst + mini.stats_off, sb, 0, peer, comm, (cudaStream_t)stream);
+  }
+  const int erc = n->group_end();
+  if (nrc || erc) return nccl_fail(n, nrc ? nrc : erc, "ncclSend/ncclRecv exchange");
+  // 3b. merge my rows into their place in the outputs
+  float* my_val = topk_val + (size_t)rank * rows * k;
+  int64_t* my_idx = topk_idx + (size_t)rank * rows * k;
+  float* my_stats = row_stats + (size_t)rank * rows * 4;
+  cudaError_t e = launch_merge_ranks((const float*)(area + mini.val_off),
+                                     (const int64_t*)(area + mini.idx_off),
+                                     (const float*)(area + mini.stats_off), mini.bytes, mini.bytes,
+                                     mini.bytes, world, rows, k, my_val, my_idx, my_stats,
                                      (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "merge launch");
-  if (Q) g_launches++;
+  g_launches++;
+  // 4b. all-gather the merged rows in place
+  nrc = n->group_start();
+  if (!nrc) nrc = n->allgather(my_val, topk_val, vb, 0, comm, (cudaStream_t)stream);
+  if (!nrc) nrc = n->allgather(my_idx, topk_idx, ib, 0, comm, (cudaStream_t)stream);
+  if (!nrc) nrc = n->allgather(my_stats, row_stats, sb, 0, comm, (cudaStream_t)stream);
+  const int erc2 = n->group_end();
+  if (nrc || erc2) return nccl_fail(n, nrc ? nrc : erc2, "ncclAllGather of the merged rows");
   return MCL_OK;
 }
 
@@ -414,6 +473,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 2) return g_opt_simt.exchange(value);
   if (opt == 3) return g_opt_timing.exchange(value);
   if (opt == 4) return g_opt_cluster.exchange(value);
+  if (opt == 5) return g_opt_allgather.exchange(value);
   return -1;
 }
 

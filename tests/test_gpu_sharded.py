@@ -66,11 +66,13 @@ def test_world1_sharded_equals_plain(lib_built):
     torch.testing.assert_close(out.stats, full.stats, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_two_rank_nccl_sharded_equals_unsharded(lib_built):
+@pytest.mark.parametrize("world", [2, 4])      # 2: all-gather merge; 4: row-exchange merge
+def test_multi_rank_nccl_sharded_equals_unsharded(lib_built, world):
     import torch.multiprocessing as mp
-    world, port = 2, _free_port()
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    port = _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-        assert dict(ret) == {0: "ok", 1: "ok"}
+        assert dict(ret) == {r: "ok" for r in range(world)}
