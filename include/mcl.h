@@ -186,7 +186,8 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
  * through the CUDA-core check kernel instead of tcgen05 (tests only), 3 = record per-CTA
  * start/end globaltimer stamps in the first 16 KB of the workspace, 4 = 1 disables the CTA-pair
  * multicast of table tiles, 5 = 1 forces the plain all-gather merge in the sharded scan (default:
- * row exchange for world > 2).  Returns the old value.
+ * row exchange for world > 2), 6 = 1 times the phases of every scan with CUDA events (debug,
+ * synchronises); opt 100..102 read the last memset / scan / merge time in ns.  Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);
 

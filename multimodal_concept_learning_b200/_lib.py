@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcl_sm100.so")
+# MCL_LIB_PATH: load an experiment build instead (A/B timing of kernel variants only)
+LIB_PATH = os.environ.get("MCL_LIB_PATH") or os.path.join(_HERE, "libmcl_sm100.so")
 
 MCL_DTYPE_BF16, MCL_DTYPE_F32 = 0, 1
 MCL_MAX_K = 64

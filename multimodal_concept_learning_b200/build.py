@@ -37,10 +37,12 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()) -> str:
+    """`out` / `defines` build experiment variants beside the product library (A/B timing)."""
+    if out == LIB and not defines and not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out,
+           *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), flush=True)
@@ -49,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed with exit code {res.returncode}")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

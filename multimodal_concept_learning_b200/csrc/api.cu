@@ -16,7 +16,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0};
+std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
+float g_phase_ms[3] = {0.f, 0.f, 0.f};   // last scan: memset, scan kernel, merge kernel (option 6)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -131,10 +132,17 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
              g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap};
   int merge_split = 1;
   cudaError_t e;
+  const bool phases = g_opt_phase.load() != 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (phases) {
+    for (auto& x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], stream);
+  }
   if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
     char msg[256] = "";
     e = cudaMemsetAsync(ws.tau_shared, 0, ws.zero_bytes, stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset of the shared thresholds");
+    if (phases) cudaEventRecord(ev[1], stream);
     e = launch_scan_tc(a, sch, ws.sv, stream, msg, sizeof(msg));
     if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);
     merge_split = sch.ng * 2;
@@ -144,9 +152,17 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
     merge_split = nsplit;
   }
   g_launches++;
+  if (phases) cudaEventRecord(ev[2], stream);
   e = launch_merge_slots(ws.sv, merge_split, Q, k, inv_q, scale, softcap, index_base, topk_val, topk_idx, row_stats, stream);
   if (e != cudaSuccess) return cuda_fail(e, "merge launch");
   g_launches++;
+  if (phases) {   // debug only: synchronises
+    cudaEventRecord(ev[3], stream);
+    cudaEventSynchronize(ev[3]);
+    if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load())
+      for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&g_phase_ms[i], ev[i], ev[i + 1]);
+    for (auto& x : ev) cudaEventDestroy(x);
+  }
   return MCL_OK;
 }
 
@@ -474,6 +490,8 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 3) return g_opt_timing.exchange(value);
   if (opt == 4) return g_opt_cluster.exchange(value);
   if (opt == 5) return g_opt_allgather.exchange(value);
+  if (opt == 6) return g_opt_phase.exchange(value);
+  if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }
 

@@ -11,7 +11,10 @@ namespace mcl {
 constexpr int kBlockM = 128;        // query rows per CTA tile  (UMMA M, TMEM lanes)
 constexpr int kBlockN = 256;        // table rows per tile      (UMMA N, TMEM columns)
 constexpr int kBlockK = 64;         // bf16 per K slice = 128 B = one SWIZZLE_128B row
-constexpr int kCandCap = 128;       // candidate-buffer entries per query row and slot
+#ifndef MCL_CAND_CAP
+#define MCL_CAND_CAP 128
+#endif
+constexpr int kCandCap = MCL_CAND_CAP;  // candidate-buffer entries per query row and slot
 constexpr int kChunk = 32;          // score columns one tcgen05.ld hands a thread
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -39,7 +42,7 @@ __host__ __device__ __forceinline__ float key2f(uint32_t k) {
 // and (m, s, sum_z, z_label) over that range.  Slots live in the caller's workspace.
 struct SlotView {
   uint2* cand;   // [nslots][kBlockM][kCandCap]  (.x = float bits of y, .y = local row)
-  int* cnt;      // [nslots][kBlockM]
+  int2* cnt;     // [nslots][kBlockM]  (.x = entries, .y = key of the row's final threshold)
   float4* stats; // [nslots][kBlockM]
 };
 

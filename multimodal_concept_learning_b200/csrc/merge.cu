@@ -4,6 +4,7 @@
 // two per lane, and is updated by warp-shuffle bitonic networks.  Keys are 64 bit:
 // high word = order-preserving float key, low word = ~row index, so a plain descending
 // sort realises "value desc, index asc" -- the documented lowest-index-wins tie rule.
+#include <atomic>
 #include "kernels.h"
 
 namespace mcl {
@@ -71,26 +72,38 @@ struct TopList {
   }
 };
 
-// One CTA (4 warps) per query row.  Warp w folds slots w, w+4, ... into its own running
-// top-64; candidates that cannot beat the warp's current k-th key are dropped before any
-// sorting (after the first slot almost all are), survivors are batched 64 at a time through
-// a small shared-memory queue.  Warp 0 then folds the other warps' lists and writes the row.
+// kWPR warps per query row (1 for the usual handful of slots, 16 when a small Q was split over
+// all SMs).  Phase A: the largest threshold any slot recorded for the row is a lower bound of
+// its global k-th best, so only candidates at or above it can matter -- typically ~2k of the
+// up to 128 per slot -- and everything else is dropped without being sorted.  Phase B: each
+// warp folds its slots' survivors, 64 at a time through a shared-memory queue, into a running
+// sorted top-64.  Phase C (kWPR > 1): warp 0 folds the other warps' lists and writes the row.
 constexpr int kPendCap = 96;
 
-template <int kMergeWarps>
-__global__ void __launch_bounds__(32 * kMergeWarps)
+template <int kWPR>
+__global__ void __launch_bounds__(128 > 32 * kWPR ? 128 : 32 * kWPR)
 merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restrict__ inv_q,
                    float scale, float softcap, long long index_base, float* __restrict__ topk_val,
                    long long* __restrict__ topk_idx, float4* __restrict__ row_stats) {
-  __shared__ unsigned long long pend[kMergeWarps][kPendCap];
-  __shared__ unsigned long long lists[kMergeWarps][64];
+  constexpr int kWarps = (128 > 32 * kWPR ? 128 : 32 * kWPR) / 32;
+  constexpr int kRows = kWarps / kWPR;                  // rows per CTA
+  __shared__ unsigned long long pend[kWarps][kPendCap];
+  __shared__ unsigned long long lists[kWarps][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x;
-  const int rb = row / kBlockM, r_in = row % kBlockM;
+  const int wr = warp % kWPR;                           // this warp's rank within its row
+  const int row = blockIdx.x * kRows + warp / kWPR;
+  const bool live = row < Q;
+  const int rb = live ? row / kBlockM : 0, r_in = live ? row % kBlockM : 0;
   const int slot0 = rb * nsplit;
   const unsigned lt = (1u << lane) - 1u;
 
-  if (warp == 0) {   // (m, s, sum_z, z_label) over the slots
+  // ---- phase A: bound, and (warp 0 of the row) the merged statistics ---------------------
+  uint32_t bound = 0u;
+  if (live)
+    for (int i = lane; i < nsplit; i += 32)
+      bound = max(bound, (uint32_t)sv.cnt[(size_t)(slot0 + i) * kBlockM + r_in].y);
+  bound = __reduce_max_sync(0xffffffffu, bound);
+  if (live && wr == 0) {
     float m = -INFINITY;
     for (int i = lane; i < nsplit; i += 32)
       m = fmaxf(m, sv.stats[(size_t)(slot0 + i) * kBlockM + r_in].x);
@@ -112,7 +125,8 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
     if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
   }
 
-  const float rs = (inv_q ? inv_q[row] : 1.f) * scale;
+  // ---- phase B ----------------------------------------------------------------------------
+  const float rs = live ? (inv_q ? inv_q[row] : 1.f) * scale : 1.f;
   TopList top; top.init();
   unsigned long long kth = 0ull;          // key of the warp's current k-th best (0 = none yet)
   int npend = 0;
@@ -128,42 +142,49 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
     const int p = k - 1;
     kth = shfl64(p < 32 ? top.r0 : top.r1, p & 31);
   };
-  for (int i = warp; i < nsplit; i += kMergeWarps) {
-    const int slot = slot0 + i;
-    const int n = sv.cnt[(size_t)slot * kBlockM + r_in];
-    const uint2* b = sv.cand + ((size_t)slot * kBlockM + r_in) * kCandCap;
-    for (int base = 0; base < n; base += 32) {
-      const int j = base + lane;
-      unsigned long long key = 0ull;
-      // rank by the OUTPUT value z = y * rs (what callers and the rank merge see), so that
-      // scores whose z round to the same float tie-break by table row everywhere
-      if (j < n) {
-        const uint2 e = b[j];
-        float z = __uint_as_float(e.x) * rs;
-        if (softcap > 0.f) z = softcap * tanhf(z / softcap);
-        key = pack_key(z, e.y);
+  if (live) {
+    for (int i = wr; i < nsplit; i += kWPR) {
+      const int slot = slot0 + i;
+      const int n = sv.cnt[(size_t)slot * kBlockM + r_in].x;
+      const uint2* b = sv.cand + ((size_t)slot * kBlockM + r_in) * kCandCap;
+      for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        unsigned long long key = 0ull;
+        if (j < n) {
+          const uint2 e = b[j];
+          if (f2key(__uint_as_float(e.x)) >= bound) {   // can still be among the row's k best
+            // rank by the OUTPUT value z (what callers and the rank merge see), so that scores
+            // whose z round to the same float tie-break by table row everywhere
+            float z = __uint_as_float(e.x) * rs;
+            if (softcap > 0.f) z = softcap * tanhf(z / softcap);
+            key = pack_key(z, e.y);
+          }
+        }
+        const bool keep = key > kth;      // keys are unique, so > loses nothing
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) q[npend + __popc(km & lt)] = key;
+        npend += __popc(km);
+        __syncwarp();
+        if (npend >= 64) flush64();
       }
-      const bool keep = key > kth;        // keys are unique, so > loses nothing
-      const unsigned km = __ballot_sync(0xffffffffu, keep);
-      if (keep) q[npend + __popc(km & lt)] = key;
-      npend += __popc(km);
+    }
+    if (npend > 0) {                      // tail: pad the queue to 64 with empty keys
+      if (lane + npend < 64) q[npend + lane] = 0ull;
+      if (lane + npend + 32 < 64) q[npend + 32 + lane] = 0ull;
       __syncwarp();
-      if (npend >= 64) flush64();
+      npend = 64;
+      flush64();
     }
   }
-  if (npend > 0) {                        // tail: pad the queue to 64 with empty keys
-    if (lane + npend < 64) q[npend + lane] = 0ull;
-    if (lane + npend + 32 < 64) q[npend + 32 + lane] = 0ull;
-    __syncwarp();
-    npend = 64;
-    flush64();
+  // ---- phase C ----------------------------------------------------------------------------
+  if (kWPR > 1) {
+    lists[warp][lane] = top.r0;
+    lists[warp][32 + lane] = top.r1;
+    __syncthreads();
+    if (wr != 0) return;
+    for (int w = 1; w < kWPR; ++w) top.push_sorted(lists[warp + w][lane], lists[warp + w][32 + lane], lane);
   }
-  lists[warp][lane] = top.r0;
-  lists[warp][32 + lane] = top.r1;
-  __syncthreads();
-  if (warp != 0) return;
-  for (int w = 1; w < kMergeWarps; ++w) top.push_sorted(lists[w][lane], lists[w][32 + lane], lane);
-
+  if (!live) return;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int p = i * 32 + lane;
@@ -238,13 +259,27 @@ cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s) {
   if (Q == 0) return cudaSuccess;
+  // Same shared-memory carve-out as the scan kernel that precedes this one in every step:
+  // alternating carve-outs makes the SMs drain and reconfigure before each launch.
+  static std::atomic<bool> pref_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !pref_set[dev].load()) {
+    cudaFuncSetAttribute(merge_slots_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(merge_slots_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(merge_ranks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    pref_set[dev].store(true);
+  }
   // few rows with many slots (small Q split over all SMs): more warps per row
   if (nsplit > 32 && Q <= 4096)
     merge_slots_kernel<16><<<(unsigned)Q, 32 * 16, 0, s>>>(
         sv, nsplit, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   else
-    merge_slots_kernel<4><<<(unsigned)Q, 32 * 4, 0, s>>>(
+    merge_slots_kernel<1><<<(unsigned)((Q + 3) / 4), 128, 0, s>>>(
         sv, nsplit, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   return cudaGetLastError();

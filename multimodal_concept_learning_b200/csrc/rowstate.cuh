@@ -239,9 +239,11 @@ __device__ __forceinline__ void row_apply_shared_tau(RowState& st, uint32_t shar
 
 // Close a slot: candidate count and (m, s, sum_z, z_label) in z space for this row.
 // softcap c > 0: z' = c*tanh(z/c); sum_y already holds the sum of tanh values.
-__device__ __forceinline__ void row_flush(const RowState& st, float rs, float softcap, int* cnt_out,
+// The row's final threshold travels with the count: it is a lower bound of the row's global
+// k-th best score, which lets the merge drop most candidates of the OTHER slots unsorted.
+__device__ __forceinline__ void row_flush(const RowState& st, float rs, float softcap, int2* cnt_out,
                                           float4* stats_out) {
-  *cnt_out = st.cnt;
+  *cnt_out = make_int2(st.cnt, (int)f2key(st.tau));
   if (softcap > 0.f) {
     const float rc = rs / softcap;
     *stats_out = make_float4(softcap * tanhf(st.m * rc), st.s, softcap * st.sum_y,

@@ -109,7 +109,7 @@ scan_simt_kernel(const T* __restrict__ q, const T* __restrict__ table, int Q, in
       else row_process_chunk<true, false>(st, acc, col0, n_valid, a, lab_local, 0.f);
     }
     __syncwarp();
-    warp_compact_rows(st, k, warp_buf, lane, nullptr);
+    if (c + 1 < c_end) warp_compact_rows(st, k, warp_buf, lane, nullptr);   // not after the last chunk
   }
   row_flush(st, rs, softcap, sv.cnt + (size_t)slot * kBlockM + tid, sv.stats + (size_t)slot * kBlockM + tid);
 }

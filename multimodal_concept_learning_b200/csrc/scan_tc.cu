@@ -293,7 +293,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           if (n_valid == kChunk) row_process_chunk<false, kCap>(st, y, col0, kChunk, a, lab_local, rc);
           else row_process_chunk<true, kCap>(st, y, col0, n_valid, a, lab_local, rc);
           __syncwarp();
-          warp_compact_rows(st, p.k, warp_buf, lane, tau_pub);
+          // (nothing follows the last chunk of the slot: leave its buffer to the merge)
+          if (!(vt + 1 == vt1 && c + 1 == nch)) warp_compact_rows(st, p.k, warp_buf, lane, tau_pub);
         };
 
         // TMEM -> registers one chunk at a time; the other epilogue warp on this scheduler
@@ -394,7 +395,7 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
   const size_t o_tau = take((size_t)num_rb * kBlockM * sizeof(uint32_t));
   const size_t o_ctr = take((size_t)nctr * sizeof(int));
   const size_t o_cand = take((size_t)nslots * kBlockM * kCandCap * sizeof(uint2));
-  const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int));
+  const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int2));
   const size_t o_stats = take((size_t)nslots * kBlockM * sizeof(float4));
   w.bytes = off;
   w.zero_bytes = o_ctr + (((size_t)nctr * sizeof(int) + 255) & ~(size_t)255) - o_tau;
@@ -404,7 +405,7 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
     w.tau_shared = (void*)(b + o_tau);
     w.sync_ctr = (void*)(b + o_ctr);
     w.sv.cand = (uint2*)(b + o_cand);
-    w.sv.cnt = (int*)(b + o_cnt);
+    w.sv.cnt = (int2*)(b + o_cnt);
     w.sv.stats = (float4*)(b + o_stats);
   }
   return w;
@@ -427,18 +428,32 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] (pitch ld elements) -> tiles of box_rows x 64, SWIZZLE_128B
+// 2-D bf16 row-major [rows, cols] (pitch ld elements) -> tiles of box_rows x 64, SWIZZLE_128B.
+// Descriptors depend only on (base, shape, pitch, box); the last few are cached per thread
+// because the same table (and query buffer) is scanned over and over.
 static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
                       int box_rows) {
+  struct Entry { const void* base; int64_t rows, cols, ld; int box; CUtensorMap tm; bool ok; };
+  thread_local Entry cache[8] = {};
+  thread_local int next = 0;
+  for (const Entry& e : cache)
+    if (e.ok && e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.box == box_rows) {
+      *tm = e.tm;
+      return true;
+    }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  cache[next] = Entry{base, rows, cols, ld, box_rows, *tm, true};
+  next = (next + 1) % 8;
+  return true;
 }
 
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
@@ -476,26 +491,27 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   p.sync_ctr = (int*)a.sync_ctr; p.win = sch.win; p.nwin = sch.nwin;
   p.softcap = a.softcap;
   const bool cap = a.softcap > 0.f;
-  // Cooperative launch: the drift bound makes CTAs wait for one another, so all of them must
-  // be resident at once (grid <= SM count, one CTA per SM); the runtime checks exactly that.
+  // The drift bound makes CTAs wait for one another, so all of them should be resident at
+  // once: grid <= SM count with one CTA per SM (192 KB of shared memory) gives that on an
+  // otherwise idle GPU, and the wait is bounded in case foreign work holds SMs.  (A cooperative
+  // launch would enforce it, but costs ~40 us of launch latency and cannot be combined with
+  // clusters.)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sch.grid);
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = kTcSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
   attr[1].id = cudaLaunchAttributeClusterDimension;
   attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  if (cs == 2) {   // clusters: co-residency follows from grid <= SM count with one CTA per SM
+  if (cs == 2) {
     cfg.attrs = attr + 1;
     cfg.numAttrs = 1;
     return cap ? cudaLaunchKernelEx(&cfg, scan_tc_kernel<2, true>, tm_q, tm_t, p)
                : cudaLaunchKernelEx(&cfg, scan_tc_kernel<2, false>, tm_q, tm_t, p);
   }
-  cfg.numAttrs = 1;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
   return cap ? cudaLaunchKernelEx(&cfg, scan_tc_kernel<1, true>, tm_q, tm_t, p)
              : cudaLaunchKernelEx(&cfg, scan_tc_kernel<1, false>, tm_q, tm_t, p);
 }
