@@ -311,8 +311,8 @@ def main():
                        "frac": achieved / pk["bf16_tflops"], "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],
                        "peak_source": pk["source"] + " (burst cuBLAS bf16)",
                        # dram__bytes_read.sum + dram__bytes_write.sum of scan_tc_kernel<2>, one launch of this
-                       # workload at N=1, from profiles/r01_c3_scan_tc_v3_ncu_raw.csv (ncu --set full)
-                       "traffic": 4.949e9 if (args.workload == "c3" and world == 1) else None,
+                       # workload at N=1, from profiles/r01_c3_scan_tc_v6_ncu_raw.csv (ncu --set full)
+                       "traffic": 3.887e9 if (args.workload == "c3" and world == 1) else None,
                        "traffic_unit": "bytes per launch (algorithmic: %.3e)" % (
                            2.0 * (w["V"] / world * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * K_TOP + 16)),
                        "kernel": "scan_tc_kernel (per GPU; step time includes the merge kernel)"}
