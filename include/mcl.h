@@ -182,12 +182,14 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
 
 /*
  * Tuning knobs (host-side, process-global).  opt: 0 = CTAs per launch (0 = all SMs),
- * 1 = row-block group size g of the tile scheduler (0 = heuristic), 2 = route bf16 inputs
+ * 1 = row units per wave of the tile plan (0 = heuristic), 2 = route bf16 inputs
  * through the CUDA-core check kernel instead of tcgen05 (tests only), 3 = record per-CTA
- * start/end globaltimer stamps in the first 16 KB of the workspace, 4 = 1 disables the CTA-pair
- * multicast of table tiles, 5 = 1 forces the plain all-gather merge in the sharded scan (default:
+ * start/end globaltimer stamps in the first 16 KB of the workspace, 4 = 1 disables CTA pairs
+ * (cta_group::2 MMA), 5 = 1 forces the plain all-gather merge in the sharded scan (default:
  * row exchange for world > 2), 6 = 1 times the phases of every scan with CUDA events (debug,
- * synchronises); opt 100..102 read the last memset / scan / merge time in ns.  Returns the old value.
+ * synchronises), 7 = 0 plans without tail workers (default 1), 8 = tiles charged per extra
+ * segment of a tail worker (default 1); opt 100..102 read the last memset / scan / merge
+ * time in ns.  Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);
 
@@ -195,11 +197,26 @@ int64_t mcl_set_option(int opt, int64_t value);
 int64_t mcl_launch_count(void);
 
 /*
- * Host-only introspection of the tcgen05 scan's tile schedule for a device with `sm_count`
- * SMs: plan_out[10] = {row blocks, table tiles, K slices, group size g, groups ng, rounds,
- * tiles per chunk, slots, grid, 0}.  Needs no GPU (used by the CPU tests).
+ * Host-only introspection of the tcgen05 scan's tile plan (csrc/plan.h) for a device with
+ * `sm_count` SMs; needs no GPU (used by the CPU tests).  plan_out[MCL_PLAN_INTS] =
+ * {row blocks, table tiles, K slices, CTAs per worker, workers, row units per wave, row units,
+ *  waves, slot stride per row block and column half, slots, grid, drift window, drift counters
+ *  per wave, drift counters, nodes of a full wave, nodes of the last wave, then for each of the
+ *  4 + 4 node positions (first row unit, row units, first tile, first worker, groups, tiles per
+ *  group, first tail tile, tail workers, tail passes)}.
  */
+#define MCL_PLAN_INTS 88
 int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out);
+/*
+ * Every segment of that plan in execution order per worker, 6 ints each: {worker, row unit,
+ * first tile, end tile, slot of the row unit, first drift counter or -1}.  Returns the number
+ * of segments (writes at most `cap`), or a negative error code.
+ */
+int64_t mcl_plan_segments(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* segs_out,
+                          int64_t cap);
+/* The slots (column halves counted separately) the merge reads for one row block. */
+int mcl_plan_row_block_slots(int64_t Q, int64_t V_local, int64_t D, int sm_count, int64_t row_block,
+                             int32_t* first_slot, int32_t* num_slots);
 
 #ifdef __cplusplus
 }

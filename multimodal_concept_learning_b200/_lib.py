@@ -58,6 +58,9 @@ SIGNATURES = {
     "mcl_set_option": (_i64, [_i32, _i64]),
     "mcl_launch_count": (_i64, []),
     "mcl_plan_scan": (_i32, [_i64, _i64, _i64, _i32, C.POINTER(C.c_int32)]),
+    "mcl_plan_segments": (_i64, [_i64, _i64, _i64, _i32, C.POINTER(C.c_int32), _i64]),
+    "mcl_plan_row_block_slots": (_i32, [_i64, _i64, _i64, _i32, _i64, C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32)]),
 }
 
 _lib = None
@@ -80,6 +83,40 @@ def load() -> C.CDLL:
                 fn.restype, fn.argtypes = res, args
             _lib = lib
     return _lib
+
+
+PLAN_INTS = 88
+PLAN_KEYS = ["num_rb", "num_vt", "num_kb", "cs", "workers", "gu", "ru", "waves", "S", "nslots", "grid",
+             "win", "nsync", "nctr", "full_nodes", "last_nodes"]
+NODE_KEYS = ["r0", "R", "a", "w0", "nfull", "tpc", "t0", "wr", "passes"]
+
+
+def plan_scan(Q: int, V: int, D: int, sm: int = 148) -> dict:
+    """The tcgen05 scan's tile plan (csrc/plan.h) as a dict; host-only, needs no GPU."""
+    out = (C.c_int32 * PLAN_INTS)()
+    check(load().mcl_plan_scan(Q, V, D, sm, out))
+    v = list(out)
+    plan = dict(zip(PLAN_KEYS, v))
+    pos = len(PLAN_KEYS)
+    for name in ("full", "last"):
+        nodes = []
+        for i in range(4):
+            if i < plan[f"{name}_nodes"]:
+                nodes.append(dict(zip(NODE_KEYS, v[pos: pos + len(NODE_KEYS)])))
+            pos += len(NODE_KEYS)
+        plan[name] = nodes
+    return plan
+
+
+def plan_segments(Q: int, V: int, D: int, sm: int = 148) -> list:
+    """[(worker, row unit, first tile, end tile, slot of the unit, drift counter or -1)]."""
+    lib = load()
+    n = lib.mcl_plan_segments(Q, V, D, sm, None, 0)
+    if n < 0:
+        check(int(n))
+    buf = (C.c_int32 * (6 * max(1, n)))()
+    lib.mcl_plan_segments(Q, V, D, sm, buf, n)
+    return [tuple(buf[6 * i: 6 * i + 6]) for i in range(n)]
 
 
 def last_error() -> str:

@@ -17,6 +17,14 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
+std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1};
+
+PlanKnobs knobs() {
+  PlanKnobs k;
+  k.ctas = (int)g_opt_ctas.load(); k.gu = (int)g_opt_g.load(); k.cluster = (int)g_opt_cluster.load();
+  k.leftover = (int)g_opt_leftover.load(); k.seg_penalty = (int)g_opt_segpen.load();
+  return k;
+}
 float g_phase_ms[3] = {0.f, 0.f, 0.f};   // last scan: memset, scan kernel, merge kernel (option 6)
 
 int fail(int code, const char* fmt, ...) {
@@ -74,16 +82,26 @@ int simt_nsplit(int64_t Q, int64_t V, int sm) {
   return (num_chunks + cps - 1) / cps;
 }
 
-int scan_nslots(int64_t Q, int64_t V, int64_t D, int dtype, int sm, TcSchedule* sch_out,
-                int* nsplit_out) {
-  if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
-    TcSchedule s = make_tc_schedule(Q, V, D, sm, (int)g_opt_ctas.load(), (int)g_opt_g.load(), (int)g_opt_cluster.load());
-    if (sch_out) *sch_out = s;
-    return s.rounds * s.g * s.ng * 2;   // (padded row blocks) x chunks x two column halves
+bool use_tc(int dtype) { return dtype == MCL_DTYPE_BF16 && !g_opt_simt.load(); }
+
+// slot layout of one scan: the tcgen05 plan, or `nsplit` uniform slots per row block
+struct ScanLayout { bool tc; TcPlan plan; int nsplit, nslots, rows_padded, nctr; };
+ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int dtype, int sm) {
+  ScanLayout L{};
+  L.tc = use_tc(dtype);
+  const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
+  if (L.tc) {
+    L.plan = make_tc_plan(Q, V, D, sm, knobs());
+    L.nslots = plan_nslots(L.plan);
+    L.rows_padded = L.plan.ru * L.plan.cs;
+    L.nctr = plan_nctr(L.plan);
+  } else {
+    L.nsplit = simt_nsplit(Q, V, sm);
+    L.nslots = num_rb * L.nsplit;
+    L.rows_padded = num_rb;
+    L.nctr = 0;
   }
-  const int ns = simt_nsplit(Q, V, sm);
-  if (nsplit_out) *nsplit_out = ns;
-  return (int)((Q + kBlockM - 1) / kBlockM) * ns;
+  return L;
 }
 
 int check_scan_args(const void* q, const void* table, int dtype, int64_t Q, int64_t V, int64_t D,
@@ -118,19 +136,14 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   DevInfo di;
   if ((rc = require_sm100(&di))) return rc;
   if (Q == 0) return MCL_OK;
-  TcSchedule sch{};
-  int nsplit = 1;
-  const int nslots = scan_nslots(Q, V, D, dtype, di.sm, &sch, &nsplit);
-  const int num_rb = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.g
-                                                                     : (int)((Q + kBlockM - 1) / kBlockM);
-  const int nctr = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.ng * sch.nwin : 0;
-  Workspace ws = carve_workspace(workspace, nslots, num_rb, nctr);
+  const ScanLayout L = scan_layout(Q, V, D, dtype, di.sm);
+  Workspace ws = carve_workspace(workspace, L.nslots, L.rows_padded, L.nctr);
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
              g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap};
-  int merge_split = 1;
+  SlotMap map{};
   cudaError_t e;
   const bool phases = g_opt_phase.load() != 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -138,28 +151,28 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
     for (auto& x : ev) cudaEventCreate(&x);
     cudaEventRecord(ev[0], stream);
   }
-  if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) {
+  if (L.tc) {
     char msg[256] = "";
     e = cudaMemsetAsync(ws.tau_shared, 0, ws.zero_bytes, stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset of the shared thresholds");
     if (phases) cudaEventRecord(ev[1], stream);
-    e = launch_scan_tc(a, sch, ws.sv, stream, msg, sizeof(msg));
+    e = launch_scan_tc(a, L.plan, ws.sv, stream, msg, sizeof(msg));
     if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);
-    merge_split = sch.ng * 2;
+    map.stride = L.plan.S * 2; map.uniform = 0; map.plan = L.plan;
   } else {
-    e = launch_scan_simt(a, ws.sv, nsplit, stream);
+    e = launch_scan_simt(a, ws.sv, L.nsplit, stream);
     if (e != cudaSuccess) return cuda_fail(e, "scan_simt launch");
-    merge_split = nsplit;
+    map.stride = L.nsplit; map.uniform = L.nsplit;
   }
   g_launches++;
   if (phases) cudaEventRecord(ev[2], stream);
-  e = launch_merge_slots(ws.sv, merge_split, Q, k, inv_q, scale, softcap, index_base, topk_val, topk_idx, row_stats, stream);
+  e = launch_merge_slots(ws.sv, map, Q, k, inv_q, scale, softcap, index_base, topk_val, topk_idx, row_stats, stream);
   if (e != cudaSuccess) return cuda_fail(e, "merge launch");
   g_launches++;
   if (phases) {   // debug only: synchronises
     cudaEventRecord(ev[3], stream);
     cudaEventSynchronize(ev[3]);
-    if (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load())
+    if (L.tc)
       for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&g_phase_ms[i], ev[i], ev[i + 1]);
     for (auto& x : ev) cudaEventDestroy(x);
   }
@@ -281,12 +294,8 @@ size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, in
   DevInfo di;
   if (!dev_info(&di)) { cudaGetLastError(); di.sm = 148; }
   if (Q <= 0 || V_local <= 0 || D <= 0) return 256;
-  TcSchedule sch{};
-  const int nslots = scan_nslots(Q, V_local, D, dtype, di.sm, &sch, nullptr);
-  const int nctr = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.ng * sch.nwin : 0;
-  const int num_rb = (dtype == MCL_DTYPE_BF16 && !g_opt_simt.load()) ? sch.rounds * sch.g
-                                                                     : (int)((Q + kBlockM - 1) / kBlockM);
-  return carve_workspace(nullptr, nslots, num_rb, nctr).bytes;
+  const ScanLayout L = scan_layout(Q, V_local, D, dtype, di.sm);
+  return carve_workspace(nullptr, L.nslots, L.rows_padded, L.nctr).bytes;
 }
 
 int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
@@ -491,6 +500,8 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 4) return g_opt_cluster.exchange(value);
   if (opt == 5) return g_opt_allgather.exchange(value);
   if (opt == 6) return g_opt_phase.exchange(value);
+  if (opt == 7) return g_opt_leftover.exchange(value);
+  if (opt == 8) return g_opt_segpen.exchange(value);
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }
@@ -499,10 +510,50 @@ int64_t mcl_launch_count(void) { return g_launches.load(); }
 
 int mcl_plan_scan(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* plan_out) {
   if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || !plan_out) return fail(MCL_ERR_BAD_ARG, "bad plan args");
-  const TcSchedule s = make_tc_schedule(Q, V_local, D, sm_count, (int)g_opt_ctas.load(), (int)g_opt_g.load(), (int)g_opt_cluster.load());
-  const int32_t v[10] = {s.num_rb, s.num_vt, s.num_kb, s.g, s.ng, s.rounds, s.tpc, s.rounds * s.g * s.ng * 2,
-                         s.grid, s.win};
-  for (int i = 0; i < 10; ++i) plan_out[i] = v[i];
+  const TcPlan s = make_tc_plan(Q, V_local, D, sm_count, knobs());
+  int32_t v[MCL_PLAN_INTS] = {s.num_rb, s.num_vt, s.num_kb, s.cs, s.workers, s.gu, s.ru, s.waves, s.S,
+                              plan_nslots(s), plan_grid(s), s.win, s.nsync, plan_nctr(s), s.full.n, s.last.n};
+  int n = 16;
+  for (const Chain* c : {&s.full, &s.last})
+    for (int i = 0; i < kMaxNodes; ++i) {
+      const Node z{};
+      const Node& d = i < c->n ? c->nd[i] : z;
+      v[n++] = d.r0; v[n++] = d.R; v[n++] = d.a; v[n++] = d.w0; v[n++] = d.nfull; v[n++] = d.tpc;
+      v[n++] = d.t0; v[n++] = d.wr; v[n++] = d.passes;
+    }
+  for (int i = 0; i < MCL_PLAN_INTS; ++i) plan_out[i] = v[i];
+  return MCL_OK;
+}
+
+int64_t mcl_plan_segments(int64_t Q, int64_t V_local, int64_t D, int sm_count, int32_t* segs_out,
+                          int64_t cap) {
+  if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || cap < 0 || (cap > 0 && !segs_out))
+    return fail(MCL_ERR_BAD_ARG, "bad plan args");
+  const TcPlan s = make_tc_plan(Q, V_local, D, sm_count, knobs());
+  int64_t n = 0;
+  for (int w = 0; w < s.workers; ++w) {
+    SegIter it;
+    seg_iter_init(it, w);
+    Seg g;
+    for (; seg_iter_next(s, it, g); ++n)
+      if (n < cap) {
+        int32_t* o = segs_out + 6 * n;
+        o[0] = w; o[1] = g.unit; o[2] = g.vt0; o[3] = g.vt1; o[4] = g.j; o[5] = g.sync;
+      }
+  }
+  return n;
+}
+
+int mcl_plan_row_block_slots(int64_t Q, int64_t V_local, int64_t D, int sm_count, int64_t row_block,
+                             int32_t* first_slot, int32_t* num_slots) {
+  if (Q < 1 || V_local < 1 || D < 1 || sm_count < 1 || !first_slot || !num_slots)
+    return fail(MCL_ERR_BAD_ARG, "bad plan args");
+  const TcPlan s = make_tc_plan(Q, V_local, D, sm_count, knobs());
+  if (row_block < 0 || row_block >= s.num_rb) return fail(MCL_ERR_BAD_ARG, "row block out of range");
+  SlotMap map{};
+  map.stride = s.S * 2; map.uniform = 0; map.plan = s;
+  *first_slot = (int32_t)row_block * map.stride;
+  *num_slots = slotmap_count(map, (int)row_block);
   return MCL_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "common.cuh"
+#include "plan.h"
 
 namespace mcl {
 
@@ -20,20 +21,18 @@ struct ScanArgs {
   float* dbg_scores;         // nullable, [Q,V]
   void* timing;              // nullable, [grid][2] uint64 (tcgen05 scan only)
   void* tau_shared;          // nullable, [num_rb*128] uint32 zeroed before launch (tcgen05 scan)
-  void* sync_ctr;            // [rounds*ng*nwin] int zeroed before launch (tcgen05 scan)
+  void* sync_ctr;            // [plan_nctr] int zeroed before launch (tcgen05 scan)
   float softcap;             // 0 = off; c > 0: logits are c*tanh(z/c)
 };
 
-// Tile schedule of the tcgen05 scan (see scan_tc.cu): ng groups of g CTAs; in round r member m
-// owns row block r*g + m and group q scans table tiles [q*tpc, (q+1)*tpc); slot = rb*ng + q.
-struct TcSchedule {
-  int num_rb, num_vt, num_kb;
-  int g, ng, rounds, tpc, grid;
-  int win, nwin;   // drift bound: members of a group stay within ~2 windows of `win` tiles
-  int cluster;     // CTAs per cluster: 2 = pairs multicast the table tile halves, 1 = none
-};
-TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
-                            int force_g, int force_cluster);
+// Tile plan of the tcgen05 scan (plan.h).  ctas / gu / cluster = 0: heuristic.  leftover = 0
+// plans without tail workers (A/B measurements); seg_penalty = tiles charged per extra segment
+// of a tail worker when balancing it against the groups.
+struct PlanKnobs { int ctas = 0, gu = 0, cluster = 0, leftover = 1, seg_penalty = 1; };
+TcPlan make_tc_plan(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKnobs& knobs);
+inline int plan_nslots(const TcPlan& p) { return p.ru * p.cs * p.S * 2; }   // incl. padding row blocks
+inline int plan_nctr(const TcPlan& p) { return p.waves * p.nsync; }
+inline int plan_grid(const TcPlan& p) { return p.workers * p.cs; }
 
 struct Workspace {
   void* timing;   // [1024][2] uint64 at offset 0: per-CTA globaltimer start/end (debug option 3)
@@ -47,12 +46,12 @@ struct Workspace {
 // carve `nslots` slots out of a caller buffer (base may be null to only size it)
 Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr);
 
-cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
+cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen);
 cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, cudaStream_t s);
 
 // slots -> final [Q,k] / [Q,4]
-cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
+cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q, int k,
                                const float* inv_q, float scale, float softcap, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s);

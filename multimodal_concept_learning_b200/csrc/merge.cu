@@ -82,7 +82,7 @@ constexpr int kPendCap = 96;
 
 template <int kWPR>
 __global__ void __launch_bounds__(128 > 32 * kWPR ? 128 : 32 * kWPR)
-merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restrict__ inv_q,
+merge_slots_kernel(SlotView sv, const SlotMap map, int Q, int k, const float* __restrict__ inv_q,
                    float scale, float softcap, long long index_base, float* __restrict__ topk_val,
                    long long* __restrict__ topk_idx, float4* __restrict__ row_stats) {
   constexpr int kWarps = (128 > 32 * kWPR ? 128 : 32 * kWPR) / 32;
@@ -94,7 +94,8 @@ merge_slots_kernel(SlotView sv, int nsplit, int Q, int k, const float* __restric
   const int row = blockIdx.x * kRows + warp / kWPR;
   const bool live = row < Q;
   const int rb = live ? row / kBlockM : 0, r_in = live ? row % kBlockM : 0;
-  const int slot0 = rb * nsplit;
+  const int slot0 = rb * map.stride;
+  const int nsplit = live ? slotmap_count(map, rb) : 0;   // slots this row block really owns
   const unsigned lt = (1u << lane) - 1u;
 
   // ---- phase A: bound, and (warp 0 of the row) the merged statistics ---------------------
@@ -254,7 +255,7 @@ merge_ranks_kernel(const char* __restrict__ val_b, const char* __restrict__ idx_
   }
 }
 
-cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
+cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q, int k,
                                const float* inv_q, float scale, float softcap, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s) {
@@ -274,13 +275,13 @@ cudaError_t launch_merge_slots(const SlotView& sv, int nsplit, int64_t Q, int k,
     pref_set[dev].store(true);
   }
   // few rows with many slots (small Q split over all SMs): more warps per row
-  if (nsplit > 32 && Q <= 4096)
+  if (map.stride > 32 && Q <= 4096)
     merge_slots_kernel<16><<<(unsigned)Q, 32 * 16, 0, s>>>(
-        sv, nsplit, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
+        sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   else
     merge_slots_kernel<1><<<(unsigned)((Q + 3) / 4), 128, 0, s>>>(
-        sv, nsplit, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
+        sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   return cudaGetLastError();
 }

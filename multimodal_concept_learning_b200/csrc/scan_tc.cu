@@ -13,14 +13,14 @@
 // share each quarter and split the tile's 256 columns in halves (own row state, own slot):
 // two resident warps per scheduler hide each other's latencies.
 //
-// Scheduling: persistent CTAs in ng groups of g.  Work proceeds in rounds; in round r member m
-// of every group owns query row block r*g + m, and group q scans the q-th contiguous chunk of
-// table tiles ([q*tpc, (q+1)*tpc)).  So at any time the whole chip works on only g row blocks
-// (their query tiles stay L2 resident) and streams ng table chunks, each tile of which is
-// fetched from HBM once and hit in L2 by the other g-1 members of its group -- measured on
-// B200 this matters more than the last few percent of SM occupancy, because L2/HBM traffic
-// costs power and the kernel runs at the 1 kW cap.  Every (row block, chunk) pair ends in a
-// partial-result slot rb*ng + q; merge.cu combines the ng slots of a row block.
+// Scheduling (plan.h): persistent workers (a worker = one CTA, or a CTA pair sharing one
+// cta_group::2 MMA).  Row units are taken in waves of gu; inside a wave the workers form nfull
+// groups of one worker per row unit that walk the same table tiles side by side -- so at any
+// time the chip works on gu row units (their query tiles stay L2 resident) and streams a few
+// table positions, each tile fetched from HBM once per group -- and the workers that do not
+// fill another group share the tail tiles of all row units, so that no SM idles when the row
+// blocks do not divide the SM count.  Every segment (worker, row unit, tile range) ends in a
+// partial-result slot; merge.cu combines the slots of a row block.
 #include <cuda.h>
 #include <stdio.h>
 #include <algorithm>
@@ -40,10 +40,10 @@ constexpr uint32_t kBarBytes = 256;
 constexpr uint32_t kCsBytes = kEpiWarps * 2 * (kBlockN / 2) * 4;  // per epilogue warp: 2 x 128 table-row scales
 constexpr uint32_t kTcSmemBytes = kRingBytes + kBarBytes + kCsBytes + 1024;  // + align slack
 
+
 struct TcParams {
   int Q, V, D, k;
-  int num_rb, num_vt, num_kb;
-  int g, ng, rounds, tpc;
+  TcPlan plan;
   const float* inv_q;
   const float* inv_t;
   float scale;
@@ -52,9 +52,8 @@ struct TcParams {
   SlotView sv;
   float* dbg_scores;
   unsigned long long* timing;   // nullable: [grid][2] globaltimer at CTA start / end
-  uint32_t* tau_shared;         // [num_rb*128] order-preserving keys, zeroed before the launch
-  int* sync_ctr;                // [rounds][ng][nwin] members that started a window, zeroed
-  int win, nwin;
+  uint32_t* tau_shared;         // [padded rows] order-preserving keys, zeroed before the launch
+  int* sync_ctr;                // [plan_nctr] CTAs that started a window, zeroed
   float softcap;                // 0 = off; c > 0: logits are c*tanh(z/c) (kCap instantiation)
 };
 
@@ -114,37 +113,36 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   const uint32_t crank = (kCS > 1) ? cluster_ctarank() : 0u;
   const bool leader = (crank == 0);
 
-  // this CTA: member `member` of group `grp`; table tiles [vt0, vt1) in every round
-  const int grp = blockIdx.x / p.g, member = blockIdx.x % p.g;
-  const int vt0 = grp * p.tpc;
-  const int vt1 = min(p.num_vt, vt0 + p.tpc);
+  // every role walks this worker's segments (plan.h) with its own iterator
+  const int num_kb = p.plan.num_kb;
+  SegIter it;
+  seg_iter_init(it, (int)blockIdx.x / kCS);
+  Seg sg;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int round = 0; round < p.rounds; ++round) {
-        const int rb = round * p.g + member;
-        if (round * p.g + (member / kCS) * kCS >= p.num_rb) break;   // whole cluster idle
-        // CTAs walking this chunk with me (clusters take part as a whole)
-        const int members = ((min(p.g, p.num_rb - round * p.g) + kCS - 1) / kCS) * kCS;
-        int* ctr = p.sync_ctr + (size_t)(round * p.ng + grp) * p.nwin;
-        for (int vt = vt0; vt < vt1; ++vt) {
-          // Drift bound: the g members of a group read the same table tiles and rely on L2 to
-          // fetch each from HBM once; nothing else keeps them together, and SMs differ in
+      while (seg_iter_next(p.plan, it, sg)) {
+        const int rb = sg.unit * kCS + (int)crank;
+        const int win = p.plan.win;
+        int* ctr = sg.sync >= 0 ? p.sync_ctr + sg.sync : nullptr;
+        for (int vt = sg.vt0; vt < sg.vt1; ++vt) {
+          // Drift bound: the members of a full group read the same table tiles and rely on L2
+          // to fetch each from HBM once; nothing else keeps them together, and SMs differ in
           // speed by a few percent.  A member announces every window of `win` tiles it starts
           // and may not start window w before all members have started window w-2.
-          if ((vt - vt0) % p.win == 0) {
-            const int w = (vt - vt0) / p.win;
+          if (ctr && (vt - sg.vt0) % win == 0) {
+            const int w = (vt - sg.vt0) / win;
             atomicAdd(ctr + w, 1);
             if (w >= 2) {
               // bounded (~1 s): if a co-resident peer never shows up (SMs held by foreign work)
               // give up the L2 locality rather than hang
               const volatile int* c = ctr + (w - 2);
-              for (int spin = 0; *c < members && spin < (1 << 22); ++spin) __nanosleep(256);
+              for (int spin = 0; *c < sg.members && spin < (1 << 22); ++spin) __nanosleep(256);
             }
           }
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * kStageBytes;
             if (kCS == 1) {
@@ -168,13 +166,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCS, kBlockN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int round = 0; round < p.rounds; ++round) {
-        if (round * p.g + (member / kCS) * kCS >= p.num_rb) break;
-        for (int vt = vt0; vt < vt1; ++vt) {
+      while (seg_iter_next(p.plan, it, sg)) {
+        const int ntile = sg.vt1 - sg.vt0;
+        for (int t = 0; t < ntile; ++t) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this stage
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kBlockN;
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * kStageBytes;
@@ -222,10 +220,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                                c0 + 2 < p.V ? p.inv_t[c0 + 2] : 1.f, 1.f);
       cs_vt = vt_;
     };
-    for (int round = 0; round < p.rounds; ++round) {
-      const int rb = round * p.g + member;          // may be a padding row block inside a cluster
-      if (round * p.g + (member / kCS) * kCS >= p.num_rb || vt0 >= vt1) break;
-      slot = (rb * p.ng + grp) * 2 + half;
+    Seg nx;
+    bool have = seg_iter_next(p.plan, it, sg);
+    while (have) {
+      const bool have_next = seg_iter_next(p.plan, it, nx);
+      const int vt0 = sg.vt0, vt1 = sg.vt1;
+      const int rb = sg.unit * kCS + (int)crank;    // may be a padding row block inside a cluster
+      slot = (rb * p.plan.S + sg.j) * 2 + half;
       uint2* slot_buf = p.sv.cand + (size_t)slot * kBlockM * kCandCap;
       st.reset(slot_buf + (size_t)row_in_tile * kCandCap);
       warp_buf = slot_buf + (size_t)(quarter * 32) * kCandCap;
@@ -240,17 +241,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const long long l = lg - p.index_base;
         if (lg != -100 && l >= 0 && l < p.V) lab_local = (int)l;
       }
-      // threshold word shared by the ng CTAs that scan this query row (other table chunks)
+      // threshold word shared by all workers that scan this query row (other table tiles)
       uint32_t* tau_pub = p.tau_shared ? p.tau_shared + row : nullptr;
-      uint32_t tau_seen = 0u;
-      const bool more_rounds =
-          (round + 1 < p.rounds) && ((round + 1) * p.g + (member / kCS) * kCS < p.num_rb);
+      uint32_t tau_seen = tau_pub ? __ldcg(tau_pub) : 0u;   // later segments start below a tight bound
+      const int next_vt0 = have_next ? nx.vt0 : -1;
       for (int vt = vt0; vt < vt1; ++vt) {
         if (p.inv_t) {
           if (cs_vt != vt) load_cs(vt);                // first tile of a run: exposed once
           reinterpret_cast<float4*>(cs_warp + tb * kHalfN)[lane] = cs_ra;
           __syncwarp();
-          if (vt + 1 < vt1) load_cs(vt + 1); else if (more_rounds) load_cs(vt0);
+          if (vt + 1 < vt1) load_cs(vt + 1); else if (next_vt0 >= 0) load_cs(next_vt0);
         }
         if (tau_pub) {                                 // value read one tile ago, then re-read
           row_apply_shared_tau(st, tau_seen);
@@ -314,6 +314,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
       row_flush(st, rs, kCap ? p.softcap : 0.f, p.sv.cnt + (size_t)slot * kBlockM + row_in_tile,
                 p.sv.stats + (size_t)slot * kBlockM + row_in_tile);
+      sg = nx;
+      have = have_next;
     }
   }
 
@@ -336,54 +338,150 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 // host side
 // ---------------------------------------------------------------------------------------
 
-TcSchedule make_tc_schedule(int64_t Q, int64_t V, int64_t D, int sm_count, int force_ctas,
-                            int force_g, int force_cluster) {
-  TcSchedule s{};
-  s.num_rb = (int)((Q + kBlockM - 1) / kBlockM);
-  s.num_vt = (int)((V + kBlockN - 1) / kBlockN);
-  s.num_kb = (int)((D + kBlockK - 1) / kBlockK);
-  const int ctas = (force_ctas > 0) ? std::min(force_ctas, sm_count) : sm_count;
-  // Cost model (fitted to B200 measurements, profiles/): time = tensor time of the longest CTA
-  // + HBM traffic / bandwidth.  Traffic = one table pass per round, plus the share of the
-  // L2-level operand traffic that misses once the working set (g query blocks + ng table
-  // streams of ~4 tiles) outgrows the usable L2.
-  const double a_block = (double)kBlockM * s.num_kb * kBlockK * 2.0;
-  const double b_tile = (double)kBlockN * s.num_kb * kBlockK * 2.0;
-  const double t_tile = 2.0 * kBlockM * kBlockN * (double)s.num_kb * kBlockK / 9.0e12;
-  const double table_bytes = (double)V * (double)D * 2.0;
-  const double l2_level = (double)s.num_rb * s.num_vt * (a_block + b_tile);
-  const double l2_cap = 100.0e6, hbm_bw = 5.0e12;
-  // every round restarts the top-k filter of each row (threshold -inf -> bursts of buffer
-  // compactions while it tightens): measured 0.15-0.3 ms per round on B200
-  const double t_restart = 2.0e-4;
-  double best = 1e300;
-  int best_g = 1;
-  const int gmax = std::max(1, std::min(s.num_rb, ctas));
-  for (int g = 1; g <= gmax; ++g) {
-    const int ng = std::min(ctas / g, s.num_vt);
-    if (ng < 1) break;
-    const int rounds = (s.num_rb + g - 1) / g;
-    const int tpc = (s.num_vt + ng - 1) / ng;
-    const double ws = g * a_block + ng * 4.0 * b_tile;
-    const double miss = ws > l2_cap ? 1.0 - l2_cap / ws : 0.0;
-    const double dram = rounds * table_bytes + (double)Q * D * 2.0 + miss * l2_level;
-    double cost = rounds * (tpc * t_tile + t_restart) + dram / hbm_bw;
-    if (g % 2 != 0) cost *= 1.08;        // no CTA pairing: 48 instead of 32 KB per K slice from L2
-    if (cost < best) { best = cost; best_g = g; }
+// One node of a wave's plan (plan.h): R row units x tiles [a, T) on W >= R workers, and,
+// recursively, the nodes below it.  Returns the tiles on the critical path.
+struct NodePlan { long crit; long tiles_hbm; int n; Node nd[kMaxNodes]; };
+static NodePlan plan_node(int R, int a, int T, int W, int depth, int r0, int w0, bool tails, int pen) {
+  const int len = T - a;
+  NodePlan best{};
+  Node nd{};
+  nd.r0 = r0; nd.R = R; nd.a = a; nd.w0 = w0;
+  int nfull = std::max(1, std::min(W / R, len));
+  const int wr = W - nfull * R;
+  // even split, the other workers idle
+  nd.tpc = (len + nfull - 1) / nfull;
+  nd.nfull = (len + nd.tpc - 1) / nd.tpc;       // no group without tiles
+  nd.t0 = T; nd.wr = 0; nd.passes = 0;
+  best.crit = nd.tpc; best.tiles_hbm = len; best.n = 1; best.nd[0] = nd;
+  if (!tails || wr <= 0 || nfull >= len || depth + 1 >= kMaxNodes) return best;
+  // groups take tpc tiles each, the wr tail workers the rest of the tiles for all R row units.
+  // Perfect balance is tpc = R*len/W; every further segment of a tail worker restarts the
+  // top-k filter of its rows (cheap: the row's other slots have published a threshold by
+  // then), charged as `pen` tiles.
+  const int hi = len / nfull;
+  const int centre = (int)((long long)R * len / W);
+  for (int tpc = std::max(1, centre - 1); tpc <= std::min(hi, centre + 2); ++tpc) {
+    const int t0 = a + nfull * tpc, tl = T - t0;
+    if (tl < 1) continue;
+    const int passes = R / wr, rest = R - passes * wr;
+    long tail = (long)passes * tl + (long)pen * std::max(0, passes - 1);
+    NodePlan sub{};
+    if (rest > 0) {
+      sub = plan_node(rest, t0, T, wr, depth + 1, r0 + passes * wr, w0 + nfull * R, tails, pen);
+      tail += sub.crit + pen;
+    }
+    const long crit = std::max<long>(tpc, tail);
+    if (crit < best.crit) {
+      nd.nfull = nfull; nd.tpc = tpc; nd.t0 = t0; nd.wr = wr; nd.passes = passes;
+      best.crit = crit;
+      best.tiles_hbm = (long)nfull * tpc + (long)passes * tl + sub.tiles_hbm;
+      best.n = 1 + sub.n;
+      best.nd[0] = nd;
+      for (int i = 0; i < sub.n; ++i) best.nd[1 + i] = sub.nd[i];
+    }
   }
-  s.g = (force_g > 0) ? std::min(force_g, gmax) : best_g;
-  s.cluster = (s.g % 2 == 0 && force_cluster != 1) ? 2 : 1;   // CTA pairs share table tiles
-  s.ng = std::max(1, std::min(ctas / s.g, s.num_vt));
-  s.rounds = (s.num_rb + s.g - 1) / s.g;
-  s.tpc = (s.num_vt + s.ng - 1) / s.ng;
-  s.ng = (s.num_vt + s.tpc - 1) / s.tpc;      // drop groups that would own no tile
-  s.grid = s.ng * s.g;
+  return best;
+}
+
+static void finish_chain(const NodePlan& np, int win, Chain* ch, int* nsync, int* workers, int T) {
+  ch->n = np.n;
+  int jbase = 0, sync = 0;
+  for (int i = 0; i < np.n; ++i) {
+    Node nd = np.nd[i];
+    nd.jbase = jbase;
+    nd.sync0 = sync;
+    nd.nwin_g = (nd.tpc + win - 1) / win;
+    nd.nwin_t = nd.wr ? (T - nd.t0 + win - 1) / win : 0;
+    jbase += nd.nfull;
+    sync += nd.nfull * nd.nwin_g + nd.passes * nd.nwin_t;
+    *workers = std::max(*workers, nd.w0 + nd.nfull * nd.R + nd.wr);
+    ch->nd[i] = nd;
+  }
+  *nsync = std::max(*nsync, sync);
+}
+
+static TcPlan make_tc_plan_uncached(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKnobs& kn) {
+  TcPlan p{};
+  p.num_rb = (int)((Q + kBlockM - 1) / kBlockM);
+  p.num_vt = (int)((V + kBlockN - 1) / kBlockN);
+  p.num_kb = (int)((D + kBlockK - 1) / kBlockK);
+  const int ctas = (kn.ctas > 0) ? std::min(kn.ctas, sm_count) : sm_count;
+  // CTA pairs (one cta_group::2 MMA over two row blocks) whenever there are two row blocks
+  p.cs = (p.num_rb >= 2 && ctas >= 2 && kn.cluster != 1) ? 2 : 1;
+  const int W = std::max(1, ctas / p.cs);
+  const int T = p.num_vt;
+  p.ru = (p.num_rb + p.cs - 1) / p.cs;
+  // Cost model (fitted to B200 measurements, profiles/): time = tensor time of the critical
+  // path + HBM traffic / bandwidth.  Traffic = the table tiles each group and tail pass
+  // streams, plus the share of the L2-level operand traffic that misses once the working set
+  // (gu query units + a few table streams of ~4 tiles) outgrows the usable L2.  (The kernel
+  // runs at the board's power cap: HBM and L2 traffic cost clock, not only time.)
+  const double a_unit = (double)p.cs * kBlockM * p.num_kb * kBlockK * 2.0;
+  const double b_tile = (double)kBlockN * p.num_kb * kBlockK * 2.0;
+  const double t_tile = 2.0 * kBlockM * kBlockN * (double)p.num_kb * kBlockK / 9.0e12;
+  const double l2_level = (double)p.num_rb * T * (a_unit / p.cs + b_tile);
+  const double l2_cap = 100.0e6, hbm_bw = 5.0e12;
+  // every wave restarts the top-k filter of each row (threshold -inf -> bursts of buffer
+  // compactions while it tightens): measured 0.15-0.3 ms per wave on B200
+  const double t_restart = 2.0e-4;
+  const bool tails = kn.leftover != 0;
+  double best = 1e300;
+  int best_gu = 1;
+  const int gmax = std::max(1, std::min(p.ru, W));
+  for (int gu = 1; gu <= gmax; ++gu) {
+    const int waves = (p.ru + gu - 1) / gu;
+    const NodePlan full = plan_node(gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
+    const NodePlan last = plan_node(p.ru - (waves - 1) * gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
+    const double tiles = (double)(waves - 1) * full.crit + last.crit;
+    const int streams = std::max(full.nd[0].nfull, last.nd[0].nfull);
+    const double ws = gu * a_unit + streams * 4.0 * b_tile;
+    const double miss = ws > l2_cap ? 1.0 - l2_cap / ws : 0.0;
+    const double dram = ((double)(waves - 1) * full.tiles_hbm + last.tiles_hbm) * b_tile +
+                        (double)Q * D * 2.0 + miss * l2_level;
+    double cost = tiles * t_tile + waves * t_restart + dram / hbm_bw;
+    if (p.cs == 1) cost *= 1.08;         // no CTA pairing: 48 instead of 32 KB per K slice from L2
+    if (cost < best) { best = cost; best_gu = gu; }
+  }
+  p.gu = (kn.gu > 0) ? std::min(kn.gu, gmax) : best_gu;
+  p.waves = (p.ru + p.gu - 1) / p.gu;
+  const NodePlan full = plan_node(p.gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
+  const NodePlan last = plan_node(p.ru - (p.waves - 1) * p.gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
   // window of the drift bound: ~3 windows of every stream must fit in the L2 share left
-  // after the resident query blocks
-  const double l2_stream = std::max(8.0e6, 90.0e6 - s.g * a_block);
-  s.win = (int)std::max(1.0, std::min(16.0, l2_stream / (3.0 * b_tile * s.ng)));
-  s.nwin = (s.tpc + s.win - 1) / s.win;
-  return s;
+  // after the resident query units
+  const int streams = std::max(last.nd[0].nfull, p.waves > 1 ? full.nd[0].nfull : 0);
+  const double l2_stream = std::max(8.0e6, 90.0e6 - p.gu * a_unit);
+  p.win = (int)std::max(1.0, std::min(16.0, l2_stream / (3.0 * b_tile * streams)));
+  p.nsync = 0;
+  p.workers = 0;
+  finish_chain(last, p.win, &p.last, &p.nsync, &p.workers, T);
+  if (p.waves > 1) finish_chain(full, p.win, &p.full, &p.nsync, &p.workers, T);
+  else p.full = p.last;
+  p.S = 1;
+  for (int w = (p.waves > 1 ? 0 : 1); w < 2; ++w) {   // slot stride: the widest row unit
+    const int u0 = w ? (p.waves - 1) * p.gu : 0;
+    const int rw = w ? p.ru - u0 : p.gu;
+    for (int u = 0; u < rw; ++u) p.S = std::max(p.S, plan_unit_slots(p, u0 + u));
+  }
+  return p;
+}
+
+// Planning tries every wave size with a small recursive search: cached, because the same few
+// shapes are scanned over and over.
+TcPlan make_tc_plan(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKnobs& kn) {
+  struct Key { int64_t Q, V, D; int sm; PlanKnobs kn; };
+  struct Entry { Key k; TcPlan p; bool ok; };
+  thread_local Entry cache[16] = {};
+  thread_local int next = 0;
+  auto same = [&](const Key& k) {
+    return k.Q == Q && k.V == V && k.D == D && k.sm == sm_count && k.kn.ctas == kn.ctas && k.kn.gu == kn.gu &&
+           k.kn.cluster == kn.cluster && k.kn.leftover == kn.leftover && k.kn.seg_penalty == kn.seg_penalty;
+  };
+  for (const Entry& e : cache)
+    if (e.ok && same(e.k)) return e.p;
+  Entry e{Key{Q, V, D, sm_count, kn}, make_tc_plan_uncached(Q, V, D, sm_count, kn), true};
+  cache[next] = e;
+  next = (next + 1) % 16;
+  return e.p;
 }
 
 Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
@@ -456,7 +554,7 @@ static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t c
   return true;
 }
 
-cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotView& sv,
+cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen) {
   // the opt-in to > 48 KB of dynamic shared memory is per device
   static std::atomic<bool> attr_set[64];
@@ -472,7 +570,7 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(smem=%u)", kTcSmemBytes); return e; }
     attr_set[dev].store(true);
   }
-  const int cs = sch.cluster;
+  const int cs = plan.cs;
   CUtensorMap tm_q, tm_t;
   if (!make_tmap(&tm_q, a.q, a.Q, a.D, a.ldq, kBlockM) ||
       !make_tmap(&tm_t, a.table, a.V, a.D, a.ldt, kBlockN / cs)) {
@@ -482,13 +580,12 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   }
   TcParams p{};
   p.Q = (int)a.Q; p.V = (int)a.V; p.D = (int)a.D; p.k = a.k;
-  p.num_rb = sch.num_rb; p.num_vt = sch.num_vt; p.num_kb = sch.num_kb;
-  p.g = sch.g; p.ng = sch.ng; p.rounds = sch.rounds; p.tpc = sch.tpc;
+  p.plan = plan;
   p.inv_q = a.inv_q; p.inv_t = a.inv_t; p.scale = a.scale;
   p.index_base = a.index_base; p.labels = (const long long*)a.labels;
   p.sv = sv; p.dbg_scores = a.dbg_scores; p.timing = (unsigned long long*)a.timing;
   p.tau_shared = (uint32_t*)a.tau_shared;
-  p.sync_ctr = (int*)a.sync_ctr; p.win = sch.win; p.nwin = sch.nwin;
+  p.sync_ctr = (int*)a.sync_ctr;
   p.softcap = a.softcap;
   const bool cap = a.softcap > 0.f;
   // The drift bound makes CTAs wait for one another, so all of them should be resident at
@@ -497,7 +594,7 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcSchedule& sch, const SlotV
   // launch would enforce it, but costs ~40 us of launch latency and cannot be combined with
   // clusters.)
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(sch.grid);
+  cfg.gridDim = dim3(plan_grid(plan));
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = kTcSmemBytes;
   cfg.stream = s;

@@ -301,11 +301,10 @@ def concept_scan_cta_times(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None,
     Q, D = q.shape
     V = table.shape[0]
     code = _dtype_code(q)
-    plan = (C.c_int32 * 10)()
     with torch.cuda.device(dev):
         sm = device_info()[0]
-        check(lib.mcl_plan_scan(Q, V, D, sm, plan))
-        grid = plan[8]
+        plan = _lib.plan_scan(Q, V, D, sm)
+        grid = plan["grid"]
         val = torch.empty((Q, k), dtype=torch.float32, device=dev)
         idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
         stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
@@ -321,8 +320,7 @@ def concept_scan_cta_times(q: Tensor, table: Tensor, k: int, *, inv_norm_q=None,
             lib.mcl_set_option(3, old)
         torch.cuda.synchronize(dev)
     t = ws[: grid * 16].view(torch.int64).reshape(grid, 2).cpu()
-    return t, {k_: int(v) for k_, v in zip(
-        ["num_rb", "num_vt", "num_kb", "g", "ng", "rounds", "tpc", "nslots", "grid", "_"], plan)}
+    return t, plan
 
 
 @torch.library.custom_op("mcl::similarity_matrix", mutates_args=(), device_types="cuda")

@@ -82,50 +82,63 @@ def test_argument_validation_needs_no_device(lib_built):
     assert lib.mcl_sharded_gather_bytes(100, 50, 8) >= 8 * (100 * 50 * 12 + 1600)
 
 
-def _plan(lib, Q, V, D, sm=148):
-    out = (C.c_int32 * 10)()
-    assert lib.mcl_plan_scan(Q, V, D, sm, out) == 0
-    keys = ["num_rb", "num_vt", "num_kb", "g", "ng", "rounds", "tpc", "nslots", "grid", "_"]
-    return dict(zip(keys, list(out)))
-
-
 @pytest.mark.parametrize("shape", [(16, 50257, 768), (4096, 49408, 768), (8192, 152064, 3584),
                                    (65536, 128256, 4096), (32768, 1048576, 1024), (8192, 19008, 3584),
-                                   (1, 1, 8), (129, 257, 72), (700, 3000, 64)])
-@pytest.mark.parametrize("sm", [148, 5])
-def test_schedule_covers_every_tile_once(lib_built, shape, sm):
-    """Python restatement of the kernel's round/chunk walk and of merge.cu's slot map."""
+                                   (1, 1, 8), (129, 257, 72), (700, 3000, 64), (300, 5000, 768),
+                                   (8192, 76032, 3584), (1000, 262235, 1152), (32768, 1000000, 1024)])
+@pytest.mark.parametrize("sm", [148, 5, 1])
+@pytest.mark.parametrize("leftover", [1, 0])
+def test_plan_covers_every_tile_once(lib_built, shape, sm, leftover):
+    """The tile plan (csrc/plan.h) through the same functions the scan kernel and the merge
+    kernel evaluate: every (row block, table tile) is scanned exactly once, no two segments
+    share a slot, and the merge's slot map names exactly the slots that were written."""
     from multimodal_concept_learning_b200 import _lib
     lib = _lib.load()
     Q, V, D = shape
-    p = _plan(lib, Q, V, D, sm)
+    old = lib.mcl_set_option(7, leftover)
+    try:
+        p = _lib.plan_scan(Q, V, D, sm)
+        segs = _lib.plan_segments(Q, V, D, sm)
+        slots_of = {}
+        for rb in range(p["num_rb"]):
+            a, b = C.c_int32(), C.c_int32()
+            assert lib.mcl_plan_row_block_slots(Q, V, D, sm, rb, C.byref(a), C.byref(b)) == 0
+            slots_of[rb] = (a.value, b.value)
+    finally:
+        lib.mcl_set_option(7, old)
     assert p["num_rb"] == -(-Q // 128) and p["num_vt"] == -(-V // 256) and p["num_kb"] == -(-D // 64)
-    assert 1 <= p["grid"] <= sm and p["grid"] == p["ng"] * p["g"]
-    assert p["rounds"] * p["g"] >= p["num_rb"] and p["ng"] * p["tpc"] >= p["num_vt"]
-    assert (p["ng"] - 1) * p["tpc"] < p["num_vt"], "a group without tiles would leave its slots unwritten"
-    assert p["nslots"] == p["rounds"] * p["g"] * p["ng"] * 2   # (padded row blocks) x chunks x column halves
-    g, ng, tpc, nvt = p["g"], p["ng"], p["tpc"], p["num_vt"]
-    tiles = {}
-    for cta in range(p["grid"]):
-        grp, member = divmod(cta, g)
-        for rnd in range(p["rounds"]):
-            rb = rnd * g + member
-            if rb >= p["num_rb"]:
-                break
-            for half in (0, 1):                          # warps 2-5 / 6-9: columns 0-127 / 128-255
-                slot = (rb * ng + grp) * 2 + half
-                assert slot not in tiles, "two CTAs write one slot"
-                tiles[slot] = (rb, half, list(range(grp * tpc, min(nvt, (grp + 1) * tpc))))
-    assert len(tiles) == p["num_rb"] * ng * 2
-    nsplit = ng * 2                                     # merge side: slots rb*nsplit .. +nsplit-1
+    cs, S = p["cs"], p["S"]
+    assert cs in (1, 2) and p["ru"] == -(-p["num_rb"] // cs)
+    assert 1 <= p["grid"] <= sm and p["grid"] == p["workers"] * cs
+    assert p["nslots"] == p["ru"] * cs * S * 2
+    written = {}                       # slot -> (row block, column half, tiles)
+    per_worker = {}
+    for w, unit, vt0, vt1, j, sync in segs:
+        assert 0 <= w < p["workers"] and 0 <= unit < p["ru"] and 0 <= vt0 < vt1 <= p["num_vt"]
+        assert 0 <= j < S and -1 <= sync < max(1, p["nctr"])
+        per_worker[w] = per_worker.get(w, 0) + (vt1 - vt0)
+        for crank in range(cs):
+            rb = unit * cs + crank
+            for half in (0, 1):        # warps 2-5 / 6-9: columns 0-127 / 128-255 of every tile
+                slot = (rb * S + j) * 2 + half
+                assert slot not in written, "two segments write one slot"
+                written[slot] = (rb, half, list(range(vt0, vt1)))
+    assert len(per_worker) == p["workers"], "a launched worker has no work"
     for rb in range(p["num_rb"]):
+        slot0, n = slots_of[rb]
+        assert slot0 == rb * S * 2 and 2 <= n <= S * 2
         cover = {0: [], 1: []}
-        for i in range(nsplit):
-            owner, half, t = tiles[rb * nsplit + i]
-            assert owner == rb and t, "empty or foreign slot"
+        for i in range(n):
+            owner, half, t = written[slot0 + i]
+            assert owner == rb and half == i % 2 and t
             cover[half] += t
-        assert cover[0] == cover[1] == list(range(nvt)), f"row block {rb} tiles not covered exactly once"
-    # efficiency of the chosen schedule at full SM count: within 20% of perfect balance
+        assert sorted(cover[0]) == sorted(cover[1]) == list(range(p["num_vt"])), \
+            f"row block {rb}: tiles not covered exactly once"
+        assert all(slot0 + i not in written for i in range(n, S * 2)), "written slot the merge skips"
+    # balance of the chosen plan at full SM count
+    crit = max(per_worker.values())
     if sm == 148 and p["num_rb"] * p["num_vt"] >= 148 * 8:
-        ideal = p["num_rb"] * p["num_vt"] / 148.0
-        assert p["rounds"] * p["tpc"] <= 1.2 * ideal + 1, p
+        ideal = p["ru"] * p["num_vt"] / (148 // cs)
+        assert crit <= (1.04 if leftover else 1.2) * ideal + 2, (p, crit, ideal)
+
+
