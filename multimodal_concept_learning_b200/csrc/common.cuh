@@ -106,13 +106,39 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const void* t
       "l"(tmap), "r"(bar & kPeerBitMask), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster.  Default (release.cta)
+// semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): the tcgen05.ld results the arrival
+// publishes are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync; a
+// cluster-scope release would add a memory barrier (ERRBAR, ~3 % of the epilogue's stalls).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar),
       "r"(rank)
       : "memory");
+}
+// Wait with back-off, for the single-thread producer / MMA roles: a failed try_wait (which
+// already suspends for a hardware time slice) is followed by a short sleep, so that a role
+// with nothing to do leaves its scheduler's issue slots to the epilogue warps it shares it with.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(40);
+  }
+}
+// ld.global.cg that stays where it is written (a plain __ldcg may be sunk to its use)
+__device__ __forceinline__ uint32_t ld_cg_u32_pinned(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

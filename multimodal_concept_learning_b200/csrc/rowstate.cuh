@@ -63,9 +63,15 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
     for (int i = 0; i < kChunk; ++i)
       if (i >= n_valid) y[i] = -INFINITY;
   }
-  float cm = y[0];
+  // maxima of the four groups of 8 columns (they also steer the candidate append below)
+  float gm[kChunk / 8];
 #pragma unroll
-  for (int i = 1; i < kChunk; ++i) cm = fmaxf(cm, y[i]);
+  for (int g = 0; g < kChunk / 8; ++g) {
+    const float m01 = fmaxf(y[8 * g], y[8 * g + 1]), m23 = fmaxf(y[8 * g + 2], y[8 * g + 3]);
+    const float m45 = fmaxf(y[8 * g + 4], y[8 * g + 5]), m67 = fmaxf(y[8 * g + 6], y[8 * g + 7]);
+    gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+  }
+  const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
 
   // label column (at most once per row and slot)
   if (lab_local >= col0 && lab_local < col0 + kChunk) {
@@ -75,18 +81,19 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
       if (i == off) st.y_label = y[i];
   }
 
-  // online log-sum-exp in base 2
+  // online log-sum-exp in base 2; four partial sums keep the FADD chains short (two resident
+  // warps per scheduler cannot hide a 32-deep dependent chain)
   const float m_new = fmaxf(st.m, cm);
-  float acc = 0.f, sy = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f};
   if (!CAP) {
     const float corr = ex2_fast((st.m - m_new) * a);  // first chunk: exp2(-inf) = 0, s is 0 anyway
     const float mb = m_new * a;
 #pragma unroll
     for (int i = 0; i < kChunk; ++i) {
-      acc += ex2_fast(fmaf(y[i], a, -mb));            // masked columns: exp2(-inf) = 0
-      if (TAIL) sy += (i < n_valid) ? y[i] : 0.f; else sy += y[i];
+      acc[i & 3] += ex2_fast(fmaf(y[i], a, -mb));     // masked columns: exp2(-inf) = 0
+      if (TAIL) sy[i & 3] += (i < n_valid) ? y[i] : 0.f; else sy[i & 3] += y[i];
     }
-    st.s = fmaf(st.s, corr, acc);
+    st.s = fmaf(st.s, corr, (acc[0] + acc[1]) + (acc[2] + acc[3]));
   } else {
     const float mt_new = tanhf(m_new * rc);
     const float corr = ex2_fast((tanhf(st.m * rc) - mt_new) * a);   // first chunk: s is 0
@@ -95,21 +102,28 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
     for (int i = 0; i < kChunk; ++i) {
       const float t = tanhf(y[i] * rc);
       const float e = ex2_fast(fmaf(t, a, -mb));
-      if (TAIL) { acc += (i < n_valid) ? e : 0.f; sy += (i < n_valid) ? t : 0.f; }
-      else { acc += e; sy += t; }
+      if (TAIL) { acc[i & 3] += (i < n_valid) ? e : 0.f; sy[i & 3] += (i < n_valid) ? t : 0.f; }
+      else { acc[i & 3] += e; sy[i & 3] += t; }
     }
-    st.s = fmaf(st.s, corr, acc);
+    st.s = fmaf(st.s, corr, (acc[0] + acc[1]) + (acc[2] + acc[3]));
   }
   st.m = m_new;
-  st.sum_y += sy;
+  st.sum_y += (sy[0] + sy[1]) + (sy[2] + sy[3]);
 
-  // lazy-threshold candidate append
+  // lazy-threshold candidate append.  In steady state a warp's 32 rows hold one or two
+  // candidates per chunk between them: only the groups of 8 columns that contain one run
+  // the store sequence (column order is kept: the tie rule relies on it).
   if (cm > st.tau) {
 #pragma unroll
-    for (int i = 0; i < kChunk; ++i) {
-      if (y[i] > st.tau) {
-        st.buf[st.cnt] = make_uint2(__float_as_uint(y[i]), (uint32_t)(col0 + i));
-        ++st.cnt;
+    for (int g = 0; g < kChunk / 8; ++g) {
+      if (gm[g] > st.tau) {
+#pragma unroll
+        for (int i = 8 * g; i < 8 * g + 8; ++i) {
+          if (y[i] > st.tau) {
+            st.buf[st.cnt] = make_uint2(__float_as_uint(y[i]), (uint32_t)(col0 + i));
+            ++st.cnt;
+          }
+        }
       }
     }
   }

@@ -143,7 +143,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             }
           }
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_wait_backoff(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * kStageBytes;
             if (kCS == 1) {
               mbar_expect_tx(full_bar(stage), kStageBytes);
@@ -169,7 +169,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       while (seg_iter_next(p.plan, it, sg)) {
         const int ntile = sg.vt1 - sg.vt0;
         for (int t = 0; t < ntile; ++t) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this stage
+          mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this stage
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kBlockN;
           for (int kb = 0; kb < num_kb; ++kb) {
@@ -254,7 +254,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
         if (tau_pub) {                                 // value read one tile ago, then re-read
           row_apply_shared_tau(st, tau_seen);
-          tau_seen = __ldcg(tau_pub);
+          tau_seen = ld_cg_u32_pinned(tau_pub);
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();

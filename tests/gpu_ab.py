@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = {"c3": (8192, 152064, 3584), "c3/8": (8192, 19008, 3584), "c2": (4096, 49408, 768),
-          "c5s": (32768, 262144, 1024)}
+          "c5s": (32768, 262144, 1024), "e768": (4096, 494080, 768), "c1": (16, 50257, 768)}
 
 CHILD = r'''
 import sys, json, torch
