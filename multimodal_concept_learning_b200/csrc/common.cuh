@@ -117,22 +117,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
       "r"(rank)
       : "memory");
 }
-// Wait with back-off, for the single-thread producer / MMA roles: a failed try_wait (which
-// already suspends for a hardware time slice) is followed by a short sleep, so that a role
-// with nothing to do leaves its scheduler's issue slots to the epilogue warps it shares it with.
+// Wait for the single-thread producer / MMA roles: try_wait with a suspend-time hint parks the
+// thread in hardware until the phase completes (or ~1 us passes) instead of spinning, so that a
+// role with nothing to do leaves its scheduler's issue slots to the epilogue warps it shares
+// it with (the plain spin issued 14 % of all warp instructions of an epilogue-bound scan).
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    __nanosleep(40);
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAITB_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONEB_%=;\n\t"
+      "bra WAITB_%=;\n"
+      "DONEB_%=:\n\t}\n" ::"r"(bar), "r"(parity), "r"(1000u)
+      : "memory");
 }
 // ld.global.cg that stays where it is written (a plain __ldcg may be sunk to its use)
 __device__ __forceinline__ uint32_t ld_cg_u32_pinned(const uint32_t* p) {

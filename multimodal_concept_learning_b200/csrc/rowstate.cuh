@@ -50,7 +50,7 @@ struct RowState {
   }
 };
 
-// One chunk of 32 scores for this thread's row.  col0 = local table row of y[0];
+// One chunk of 32 scores for this thread's row; called by all 32 lanes of a warp, converged.  col0 = local table row of y[0];
 // n_valid < 32 only in the ragged last chunk (TAIL), whose out-of-range columns are masked.
 // CAP: tanh soft-capped logits z' = c*tanh(z/c) (Gemma-2 style heads, modeling_gemma3.py:653-656):
 // rc = rs/c, `a` = c*log2(e); max / sum-exp / sum run on t = tanh(y*rc), ranking stays on y
@@ -113,10 +113,16 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
   // lazy-threshold candidate append.  In steady state a warp's 32 rows hold one or two
   // candidates per chunk between them: only the groups of 8 columns that contain one run
   // the store sequence (column order is kept: the tie rule relies on it).
-  if (cm > st.tau) {
+  // The group decisions are made warp-wide (one REDUX of a 4-bit mask): uniform branches need
+  // no reconvergence barriers, which cost more than the predicated-off stores they would skip.
+  unsigned gmask = 0u;
+#pragma unroll
+  for (int g = 0; g < kChunk / 8; ++g) gmask |= (gm[g] > st.tau) ? (1u << g) : 0u;
+  gmask = __reduce_or_sync(0xffffffffu, gmask);
+  if (gmask) {
 #pragma unroll
     for (int g = 0; g < kChunk / 8; ++g) {
-      if (gm[g] > st.tau) {
+      if (gmask & (1u << g)) {
 #pragma unroll
         for (int i = 8 * g; i < 8 * g + 8; ++i) {
           if (y[i] > st.tau) {

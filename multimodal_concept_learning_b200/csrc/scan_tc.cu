@@ -246,15 +246,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       uint32_t tau_seen = tau_pub ? __ldcg(tau_pub) : 0u;   // later segments start below a tight bound
       const int next_vt0 = have_next ? nx.vt0 : -1;
       for (int vt = vt0; vt < vt1; ++vt) {
+        // (both consume values requested one tile ago and request the next ones; the threshold
+        // first, so that its use does not wait on the scoreboard of the loads issued just before)
+        if (tau_pub) {
+          row_apply_shared_tau(st, tau_seen);
+          tau_seen = ld_cg_u32_pinned(tau_pub);
+        }
         if (p.inv_t) {
           if (cs_vt != vt) load_cs(vt);                // first tile of a run: exposed once
           reinterpret_cast<float4*>(cs_warp + tb * kHalfN)[lane] = cs_ra;
           __syncwarp();
           if (vt + 1 < vt1) load_cs(vt + 1); else if (next_vt0 >= 0) load_cs(next_vt0);
-        }
-        if (tau_pub) {                                 // value read one tile ago, then re-read
-          row_apply_shared_tau(st, tau_seen);
-          tau_seen = ld_cg_u32_pinned(tau_pub);
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();

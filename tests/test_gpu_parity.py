@@ -193,15 +193,34 @@ def test_tc_zero_query_rows(mcl):
     assert abs(float(out.lse[0]) - math.log(4096)) < 1e-4
 
 
-@pytest.mark.parametrize("opt,value", [(1, 1), (1, 2), (1, 3), (0, 5), (0, 1)])
+@pytest.mark.parametrize("opt,value", [(1, 1), (1, 2), (1, 3), (0, 5), (0, 1), (0, 10), (7, 0)])
 def test_tc_schedules_are_equivalent(mcl, opt, value):
-    """Different tile schedules (group size / CTA count) must give identical answers."""
+    """Different tile plans (wave size / CTA count / tail workers) must give identical answers.
+    10 CTAs = 5 workers on 3 row units: one group, a tail pass and a second-level node."""
     q, t = make_inputs(700, 3000, 64, 27)
     old = mcl.set_option(opt, value)
     try:
         run_case(mcl, q, t, 50, labels=torch.randint(0, 3000, (700,)))
     finally:
         mcl.set_option(opt, old)
+
+
+@pytest.mark.parametrize("ctas", [10, 14, 22, 26])
+def test_tc_tail_workers_against_oracle(mcl, ctas):
+    """Plans with tail passes (6 passes of one tail worker; 5 tail workers + a second node of 4
+    groups) on a shape the CPU oracle still finishes: scores, top-k, statistics and loss."""
+    from multimodal_concept_learning_b200 import _lib
+    Q, V, D = 1500, 9000, 128
+    plan = _lib.plan_scan(Q, V, D, ctas)
+    if ctas in (14, 22, 26):
+        assert plan["last"][0]["wr"] > 0, "this CTA count is meant to plan tail workers"
+    q, t = make_inputs(Q, V, D, 40 + ctas)
+    old = mcl.set_option(0, ctas)
+    try:
+        run_case(mcl, q, t, 50, labels=torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(ctas)),
+                 scale=30.0)
+    finally:
+        mcl.set_option(0, old)
 
 
 def test_index_base_and_partial_labels(mcl):
