@@ -153,8 +153,9 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   }
   if (L.tc) {
     char msg[256] = "";
-    e = cudaMemsetAsync(ws.tau_shared, 0, ws.zero_bytes, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "memset of the shared thresholds");
+    e = launch_zero(ws.tau_shared, ws.zero_bytes, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "clearing the shared thresholds");
+    g_launches++;
     if (phases) cudaEventRecord(ev[1], stream);
     e = launch_scan_tc(a, L.plan, ws.sv, stream, msg, sizeof(msg));
     if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);

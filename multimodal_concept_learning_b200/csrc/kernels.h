@@ -50,6 +50,9 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
                            cudaStream_t s, char* err, size_t errlen);
 cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, cudaStream_t s);
 
+// zero `bytes` (a multiple of 16, 16-byte aligned) on the stream
+cudaError_t launch_zero(void* ptr, size_t bytes, cudaStream_t s);
+
 // slots -> final [Q,k] / [Q,4]
 cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q, int k,
                                const float* inv_q, float scale, float softcap, int64_t index_base,

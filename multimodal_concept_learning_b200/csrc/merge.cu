@@ -255,6 +255,30 @@ merge_ranks_kernel(const char* __restrict__ val_b, const char* __restrict__ idx_
   }
 }
 
+// Clears the shared thresholds and drift counters before a scan.  A kernel of our own instead
+// of cudaMemsetAsync so that it can ask for the scan kernel's shared-memory carve-out: the
+// driver's memset kernel runs with the default one, and the SMs drain and reconfigure twice
+// around it (~10-30 us per scan, the bulk of a 16-query scan's time).
+__global__ void __launch_bounds__(256) zero_words_kernel(uint4* __restrict__ p, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+cudaError_t launch_zero(void* ptr, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return cudaSuccess;
+  static std::atomic<bool> pref_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !pref_set[dev].load()) {
+    cudaFuncSetAttribute(zero_words_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    pref_set[dev].store(true);
+  }
+  const size_t n16 = bytes / 16;   // the workspace carve-up keeps both ends 256-byte aligned
+  zero_words_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>((uint4*)ptr, n16);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q, int k,
                                const float* inv_q, float scale, float softcap, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,

@@ -1,0 +1,61 @@
+"""Fixed-shape concept scan captured in a CUDA graph.
+
+The reference's own workloads score a handful of concept tokens (16-96 rows,
+`token_embedding_analysis.py:183-260`) against the vocabulary table.  At that size one scan is
+~20 us of GPU work behind ~100 us of host work (op dispatch, output allocation, five kernel
+launches), so the step is launch-bound.  Capturing the whole step -- row norms of the queries,
+threshold clear, tcgen05 scan, slot merge -- once and replaying it removes the host from the
+loop: one `cudaGraphLaunch` per step.  The kernels and their results are the ones
+:func:`concept_scan` runs; only the launch mechanism differs.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from .ops import ScanOutput, concept_scan, row_inv_norm, _require_cuda
+
+
+class GraphedConceptScan:
+    """``scan = GraphedConceptScan(table, k, Q); out = scan(q)``.
+
+    ``out`` aliases buffers owned by the graph: it is valid until the next call (clone what must
+    outlive it).  ``q`` may live on the host (pinned memory makes the copy asynchronous)."""
+
+    def __init__(self, table: Tensor, k: int, Q: int, *, normalize: bool = True, scale: float = 1.0,
+                 inv_norm_t: Optional[Tensor] = None, with_labels: bool = False,
+                 label_smoothing: float = 0.0, index_base: int = 0, vocab_total: Optional[int] = None,
+                 softcap: Optional[float] = None):
+        dev = _require_cuda(table)
+        self.table = table if table.is_contiguous() else table.contiguous()
+        self.k, self.Q, self.normalize = int(k), int(Q), bool(normalize)
+        self.inv_t = inv_norm_t if inv_norm_t is not None else (row_inv_norm(self.table) if normalize else None)
+        self.q = torch.zeros((Q, table.shape[1]), dtype=table.dtype, device=dev)
+        self.labels = torch.full((Q,), -100, dtype=torch.int64, device=dev) if with_labels else None
+        kw = dict(normalize_q=normalize, normalize_t=normalize, scale=scale, labels=self.labels,
+                  label_smoothing=label_smoothing, inv_norm_t=self.inv_t, index_base=index_base,
+                  vocab_total=vocab_total, softcap=softcap)
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):          # warm-up outside the capture: one-time attribute
+                for _ in range(2):                 # calls, tensor-map encode, plan cache
+                    concept_scan(self.q, self.table, self.k, **kw)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = concept_scan(self.q, self.table, self.k, **kw)
+
+    def __call__(self, q: Tensor, labels: Optional[Tensor] = None) -> ScanOutput:
+        if tuple(q.shape) != tuple(self.q.shape):
+            raise ValueError(f"graph was captured for q {tuple(self.q.shape)}, got {tuple(q.shape)}")
+        if (labels is None) != (self.labels is None):
+            raise ValueError("labels must be given exactly when the graph was captured with_labels")
+        self.q.copy_(q, non_blocking=True)
+        if labels is not None:
+            self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.out

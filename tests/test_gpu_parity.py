@@ -315,3 +315,24 @@ def test_softcap_logits(mcl, dtype):
                              labels=labels, softcap=cap)
     assert torch.equal(plain.topk_idx, out.topk_idx) and torch.equal(plain.topk_val, out.topk_val)
     assert float(out.topk_val.max()) < cap
+
+
+@pytest.mark.parametrize("Q,with_labels", [(16, False), (96, True)])
+def test_graphed_scan_equals_direct_scan(mcl, Q, with_labels):
+    """The CUDA-graph replay runs the same kernels: bit-identical outputs, also when replayed
+    with new inputs, and against the oracle."""
+    V, D, k = 5000, 768, 50
+    _, t = make_inputs(1, V, D, 60)
+    td = t.cuda()
+    scan = mcl.GraphedConceptScan(td, k, Q, scale=20.0, with_labels=with_labels, label_smoothing=0.1)
+    for seed in (61, 62):
+        q, _ = make_inputs(Q, 1, D, seed)
+        labels = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(seed)) if with_labels else None
+        out = scan(q.cuda(), labels.cuda() if with_labels else None)
+        direct = mcl.concept_scan(q.cuda(), td, k, scale=20.0, labels=labels, label_smoothing=0.1)
+        assert torch.equal(out.topk_idx, direct.topk_idx) and torch.equal(out.topk_val, direct.topk_val)
+        assert torch.equal(out.stats, direct.stats)
+        ref = R.concept_scan_ref(q, t, k, scale=20.0, labels=labels, label_smoothing=0.1, keep_scores=True)
+        check_topk(out.topk_val, out.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-4)
+        if with_labels:
+            torch.testing.assert_close(out.loss.cpu().double(), ref.loss.double(), rtol=RTOL, atol=1e-5)
