@@ -188,7 +188,8 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
  * (cta_group::2 MMA), 5 = 1 forces the plain all-gather merge in the sharded scan (default:
  * row exchange for world > 2), 6 = 1 times the phases of every scan with CUDA events (debug,
  * synchronises), 7 = 0 plans without tail workers (default 1), 8 = tiles charged per extra
- * segment of a tail worker (default 1); opt 100..102 read the last memset / scan / merge
+ * segment of a tail worker (default 1), 9 = L2 eviction priority of the TMA loads (bit 0: query
+ * tiles evict-last, bit 1: table tiles evict-first); opt 100..102 read the last memset / scan / merge
  * time in ns.  Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);

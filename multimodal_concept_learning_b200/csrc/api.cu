@@ -17,12 +17,12 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
-std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1};
+std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
   k.ctas = (int)g_opt_ctas.load(); k.gu = (int)g_opt_g.load(); k.cluster = (int)g_opt_cluster.load();
-  k.leftover = (int)g_opt_leftover.load(); k.seg_penalty = (int)g_opt_segpen.load();
+  k.leftover = (int)g_opt_leftover.load(); k.seg_penalty = (int)g_opt_segpen.load(); k.win = (int)g_opt_win.load();
   return k;
 }
 float g_phase_ms[3] = {0.f, 0.f, 0.f};   // last scan: memset, scan kernel, merge kernel (option 6)
@@ -142,7 +142,8 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
-             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap};
+             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap,
+             (int)g_opt_l2.load()};
   SlotMap map{};
   cudaError_t e;
   const bool phases = g_opt_phase.load() != 0;
@@ -503,6 +504,8 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 6) return g_opt_phase.exchange(value);
   if (opt == 7) return g_opt_leftover.exchange(value);
   if (opt == 8) return g_opt_segpen.exchange(value);
+  if (opt == 9) return g_opt_l2.exchange(value);
+  if (opt == 10) return g_opt_win.exchange(value);
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }

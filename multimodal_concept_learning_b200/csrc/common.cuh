@@ -86,24 +86,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// L2 eviction-priority policies for TMA loads (the encodings createpolicy.fractional produces
+// for fraction 1.0; the same constants CUTLASS passes as TMA cache hints).
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+
 // 2-D TMA tile load, completion on an mbarrier (bytes counted as a transaction).
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, uint32_t bar,
-                                            int c_inner, int c_outer) {
+                                            int c_inner, int c_outer, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
-      "l"(tmap), "r"(bar), "r"(c_inner), "r"(c_outer)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar), "r"(c_inner), "r"(c_outer), "l"(policy)
       : "memory");
 }
 // 2-SM form (CTA pair, cta_group::2): the tile lands in THIS CTA's shared memory, the
 // complete_tx goes to the mbarrier at the same offset in the pair's leader (even) CTA.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const void* tmap, uint32_t bar,
-                                                int c_inner, int c_outer) {
+                                                int c_inner, int c_outer, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
-      "l"(tmap), "r"(bar & kPeerBitMask), "r"(c_inner), "r"(c_outer)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar & kPeerBitMask), "r"(c_inner), "r"(c_outer), "l"(policy)
       : "memory");
 }
 // arrive on the mbarrier at the same offset in CTA `rank` of the cluster.  Default (release.cta)

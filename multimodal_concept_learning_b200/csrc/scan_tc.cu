@@ -55,6 +55,7 @@ struct TcParams {
   uint32_t* tau_shared;         // [padded rows] order-preserving keys, zeroed before the launch
   int* sync_ctr;                // [plan_nctr] CTAs that started a window, zeroed
   float softcap;                // 0 = off; c > 0: logits are c*tanh(z/c) (kCap instantiation)
+  unsigned long long pol_q, pol_t;   // L2 eviction priority of the query / table tile loads
 };
 
 // kCS = CTAs per cluster.  kCS = 1: every CTA multiplies its own 128 x 256 tile
@@ -147,14 +148,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const uint32_t sa = smem_base + stage * kStageBytes;
             if (kCS == 1) {
               mbar_expect_tx(full_bar(stage), kStageBytes);
-              tma_load_2d(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM);
-              tma_load_2d(sa + kABytes, &tm_t, full_bar(stage), kb * kBlockK, vt * kBlockN);
+              tma_load_2d(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM, p.pol_q);
+              tma_load_2d(sa + kABytes, &tm_t, full_bar(stage), kb * kBlockK, vt * kBlockN, p.pol_t);
             } else {
               // both CTAs' bytes are counted on the leader's barrier, which its producer arms
               if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
-              tma_load_2d_2sm(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM);
+              tma_load_2d_2sm(sa, &tm_q, full_bar(stage), kb * kBlockK, rb * kBlockM, p.pol_q);
               tma_load_2d_2sm(sa + kABytes, &tm_t, full_bar(stage), kb * kBlockK,
-                              vt * kBlockN + (int)(crank * kSliceRows));
+                              vt * kBlockN + (int)(crank * kSliceRows), p.pol_t);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -341,38 +342,44 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 // ---------------------------------------------------------------------------------------
 
 // One node of a wave's plan (plan.h): R row units x tiles [a, T) on W >= R workers, and,
-// recursively, the nodes below it.  Returns the tiles on the critical path.
+// recursively, the nodes below it.  Returns the tiles on the critical path.  Every segment
+// restarts the top-k filter of its rows (threshold -inf -> bursts of buffer compactions while
+// it tightens): `cold` tiles' worth of time at the start of a wave, `warm` once the row's other
+// slots have published a threshold.  Below the top node a row unit gets at most kMaxSubGroups
+// more slots per node: every slot costs workspace, a restart and merge work.
+constexpr int kMaxSubGroups = 4;
 struct NodePlan { long crit; long tiles_hbm; int n; Node nd[kMaxNodes]; };
-static NodePlan plan_node(int R, int a, int T, int W, int depth, int r0, int w0, bool tails, int pen) {
+static NodePlan plan_node(int R, int a, int T, int W, int depth, int r0, int w0, bool tails, int cold,
+                          int warm) {
   const int len = T - a;
+  const int start = depth == 0 ? cold : warm;
   NodePlan best{};
   Node nd{};
   nd.r0 = r0; nd.R = R; nd.a = a; nd.w0 = w0;
   int nfull = std::max(1, std::min(W / R, len));
+  if (depth > 0) nfull = std::min(nfull, kMaxSubGroups);
   const int wr = W - nfull * R;
   // even split, the other workers idle
   nd.tpc = (len + nfull - 1) / nfull;
   nd.nfull = (len + nd.tpc - 1) / nd.tpc;       // no group without tiles
   nd.t0 = T; nd.wr = 0; nd.passes = 0;
-  best.crit = nd.tpc; best.tiles_hbm = len; best.n = 1; best.nd[0] = nd;
-  if (!tails || wr <= 0 || nfull >= len || depth + 1 >= kMaxNodes) return best;
+  best.crit = nd.tpc + start; best.tiles_hbm = len; best.n = 1; best.nd[0] = nd;
+  if (!tails || wr <= 0 || nfull >= len || depth + 1 >= kMaxNodes || W / R > nfull) return best;
   // groups take tpc tiles each, the wr tail workers the rest of the tiles for all R row units.
-  // Perfect balance is tpc = R*len/W; every further segment of a tail worker restarts the
-  // top-k filter of its rows (cheap: the row's other slots have published a threshold by
-  // then), charged as `pen` tiles.
+  // Perfect balance is tpc = R*len/W.
   const int hi = len / nfull;
   const int centre = (int)((long long)R * len / W);
-  for (int tpc = std::max(1, centre - 1); tpc <= std::min(hi, centre + 2); ++tpc) {
+  for (int tpc = std::max(1, centre - 2); tpc <= std::min(hi, centre + 2); ++tpc) {
     const int t0 = a + nfull * tpc, tl = T - t0;
     if (tl < 1) continue;
     const int passes = R / wr, rest = R - passes * wr;
-    long tail = (long)passes * tl + (long)pen * std::max(0, passes - 1);
+    long tail = (long)passes * (tl + warm);
     NodePlan sub{};
     if (rest > 0) {
-      sub = plan_node(rest, t0, T, wr, depth + 1, r0 + passes * wr, w0 + nfull * R, tails, pen);
-      tail += sub.crit + pen;
+      sub = plan_node(rest, t0, T, wr, depth + 1, r0 + passes * wr, w0 + nfull * R, tails, cold, warm);
+      tail += sub.crit;
     }
-    const long crit = std::max<long>(tpc, tail);
+    const long crit = std::max<long>(tpc + start, tail);
     if (crit < best.crit) {
       nd.nfull = nfull; nd.tpc = tpc; nd.t0 = t0; nd.wr = wr; nd.passes = passes;
       best.crit = crit;
@@ -422,37 +429,45 @@ static TcPlan make_tc_plan_uncached(int64_t Q, int64_t V, int64_t D, int sm_coun
   const double b_tile = (double)kBlockN * p.num_kb * kBlockK * 2.0;
   const double t_tile = 2.0 * kBlockM * kBlockN * (double)p.num_kb * kBlockK / 9.0e12;
   const double l2_level = (double)p.num_rb * T * (a_unit / p.cs + b_tile);
-  const double l2_cap = 100.0e6, hbm_bw = 5.0e12;
-  // every wave restarts the top-k filter of each row (threshold -inf -> bursts of buffer
-  // compactions while it tightens): measured 0.15-0.3 ms per wave on B200
-  const double t_restart = 2.0e-4;
+  // Usable L2 and the price of a DRAM byte, fitted to the ncu captures and option sweeps in
+  // profiles/ (C3 gu=32: 6.4-7.0 GB read; C4 gu=37 / 24: 65.8 / 41.9 GB, 54.5 / 52.1 ms).  The
+  // kernel is tensor bound, so DRAM bytes cost board power (clock), not bandwidth.
+  const double l2_cap = 110.0e6, miss_weight = 0.3, dram_price = 1.0 / 1.2e13;
+  // candidate buffers are hot too: ~1 KB per query row, slot and column half
+  const double buf_slot = (double)p.cs * 2.0 * kBlockM * 1024.0;
+  // restart of the top-k filter per segment, in tiles (see plan_node); option 8 scales it
+  const int cold = std::max(1, (int)(1.5e-4 * kn.seg_penalty / t_tile + 0.5));
+  const int warm = std::max(1, (int)(0.4e-4 * kn.seg_penalty / t_tile + 0.5));
   const bool tails = kn.leftover != 0;
   double best = 1e300;
   int best_gu = 1;
   const int gmax = std::max(1, std::min(p.ru, W));
   for (int gu = 1; gu <= gmax; ++gu) {
     const int waves = (p.ru + gu - 1) / gu;
-    const NodePlan full = plan_node(gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
-    const NodePlan last = plan_node(p.ru - (waves - 1) * gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
+    const NodePlan full = plan_node(gu, 0, T, W, 0, 0, 0, tails, cold, warm);
+    const NodePlan last = plan_node(p.ru - (waves - 1) * gu, 0, T, W, 0, 0, 0, tails, cold, warm);
     const double tiles = (double)(waves - 1) * full.crit + last.crit;
-    const int streams = std::max(full.nd[0].nfull, last.nd[0].nfull);
-    const double ws = gu * a_unit + streams * 4.0 * b_tile;
+    const NodePlan& wide = waves > 1 ? full : last;
+    const int streams = wide.nd[0].nfull;
+    const int slots = wide.nd[0].nfull + (wide.nd[0].wr ? 1 : 0);
+    const double ws = gu * (a_unit + slots * buf_slot) + streams * 4.0 * b_tile;
     const double miss = ws > l2_cap ? 1.0 - l2_cap / ws : 0.0;
     const double dram = ((double)(waves - 1) * full.tiles_hbm + last.tiles_hbm) * b_tile +
-                        (double)Q * D * 2.0 + miss * l2_level;
-    double cost = tiles * t_tile + waves * t_restart + dram / hbm_bw;
+                        (double)Q * D * 2.0 + miss_weight * miss * l2_level;
+    double cost = tiles * t_tile + dram * dram_price;
     if (p.cs == 1) cost *= 1.08;         // no CTA pairing: 48 instead of 32 KB per K slice from L2
     if (cost < best) { best = cost; best_gu = gu; }
   }
   p.gu = (kn.gu > 0) ? std::min(kn.gu, gmax) : best_gu;
   p.waves = (p.ru + p.gu - 1) / p.gu;
-  const NodePlan full = plan_node(p.gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
-  const NodePlan last = plan_node(p.ru - (p.waves - 1) * p.gu, 0, T, W, 0, 0, 0, tails, kn.seg_penalty);
+  const NodePlan full = plan_node(p.gu, 0, T, W, 0, 0, 0, tails, cold, warm);
+  const NodePlan last = plan_node(p.ru - (p.waves - 1) * p.gu, 0, T, W, 0, 0, 0, tails, cold, warm);
   // window of the drift bound: ~3 windows of every stream must fit in the L2 share left
   // after the resident query units
   const int streams = std::max(last.nd[0].nfull, p.waves > 1 ? full.nd[0].nfull : 0);
   const double l2_stream = std::max(8.0e6, 90.0e6 - p.gu * a_unit);
   p.win = (int)std::max(1.0, std::min(16.0, l2_stream / (3.0 * b_tile * streams)));
+  if (kn.win > 0) p.win = kn.win;
   p.nsync = 0;
   p.workers = 0;
   finish_chain(last, p.win, &p.last, &p.nsync, &p.workers, T);
@@ -476,7 +491,8 @@ TcPlan make_tc_plan(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKno
   thread_local int next = 0;
   auto same = [&](const Key& k) {
     return k.Q == Q && k.V == V && k.D == D && k.sm == sm_count && k.kn.ctas == kn.ctas && k.kn.gu == kn.gu &&
-           k.kn.cluster == kn.cluster && k.kn.leftover == kn.leftover && k.kn.seg_penalty == kn.seg_penalty;
+           k.kn.cluster == kn.cluster && k.kn.leftover == kn.leftover && k.kn.seg_penalty == kn.seg_penalty &&
+           k.kn.win == kn.win;
   };
   for (const Entry& e : cache)
     if (e.ok && same(e.k)) return e.p;
@@ -589,6 +605,8 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
   p.tau_shared = (uint32_t*)a.tau_shared;
   p.sync_ctr = (int*)a.sync_ctr;
   p.softcap = a.softcap;
+  p.pol_q = (a.l2_mode & 1) ? kL2EvictLast : kL2EvictNormal;
+  p.pol_t = (a.l2_mode & 2) ? kL2EvictFirst : ((a.l2_mode & 4) ? kL2EvictLast : kL2EvictNormal);
   const bool cap = a.softcap > 0.f;
   // The drift bound makes CTAs wait for one another, so all of them should be resident at
   // once: grid <= SM count with one CTA per SM (192 KB of shared memory) gives that on an

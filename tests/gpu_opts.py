@@ -15,7 +15,7 @@ from multimodal_concept_learning_b200 import _lib  # noqa: E402
 
 SHAPES = {"c1": (16, 50257, 768), "c2": (4096, 49408, 768), "c3": (8192, 152064, 3584),
           "c3/2": (8192, 76032, 3584), "c3/8": (8192, 19008, 3584), "c4": (65536, 128256, 4096),
-          "c5": (32768, 1048576, 1024), "c5s": (32768, 262144, 1024), "c5/8": (32768, 131072, 1024),
+          "c5": (32768, 1048576, 1024), "c5s": (32768, 262144, 1024), "c5/8": (32768, 131072, 1024), "c4/8": (65536, 16032, 4096),
           # epilogue-bound probes: long scans (start-up transient amortised), small / CLIP-size D
           "e64": (4096, 400000, 64), "e768": (4096, 494080, 768), "e256": (4096, 400000, 256)}
 

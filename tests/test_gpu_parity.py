@@ -205,15 +205,13 @@ def test_tc_schedules_are_equivalent(mcl, opt, value):
         mcl.set_option(opt, old)
 
 
-@pytest.mark.parametrize("ctas", [10, 14, 22, 26])
+@pytest.mark.parametrize("ctas", [10, 14, 22, 26, 38])
 def test_tc_tail_workers_against_oracle(mcl, ctas):
     """Plans with tail passes (6 passes of one tail worker; 5 tail workers + a second node of 4
     groups) on a shape the CPU oracle still finishes: scores, top-k, statistics and loss."""
     from multimodal_concept_learning_b200 import _lib
     Q, V, D = 1500, 9000, 128
-    plan = _lib.plan_scan(Q, V, D, ctas)
-    if ctas in (14, 22, 26):
-        assert plan["last"][0]["wr"] > 0, "this CTA count is meant to plan tail workers"
+    # (tests/test_boundary.py::test_small_cta_counts_plan_tail_workers keeps this list honest)
     q, t = make_inputs(Q, V, D, 40 + ctas)
     old = mcl.set_option(0, ctas)
     try:
