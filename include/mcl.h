@@ -189,7 +189,9 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
  * row exchange for world > 2), 6 = 1 times the phases of every scan with CUDA events (debug,
  * synchronises), 7 = 0 plans without tail workers (default 1), 8 = tiles charged per extra
  * segment of a tail worker (default 1), 9 = L2 eviction priority of the TMA loads (bit 0: query
- * tiles evict-last, bit 1: table tiles evict-first); opt 100..102 read the last memset / scan / merge
+ * tiles evict-last, bit 1: table tiles evict-first), 10 = drift window in tiles (0 = heuristic),
+ * 11 = 1 sends one-row-block batches through the streaming top-k path instead of the score-dump +
+ * radix-select path (tests, A/B); opt 100..102 read the last memset / scan / merge
  * time in ns.  Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);

@@ -17,7 +17,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
-std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0};
+std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
@@ -85,7 +85,12 @@ int simt_nsplit(int64_t Q, int64_t V, int sm) {
 bool use_tc(int dtype) { return dtype == MCL_DTYPE_BF16 && !g_opt_simt.load(); }
 
 // slot layout of one scan: the tcgen05 plan, or `nsplit` uniform slots per row block
-struct ScanLayout { bool tc; TcPlan plan; int nsplit, nslots, rows_padded, nctr; };
+struct ScanLayout {
+  bool tc; TcPlan plan; int nsplit, nslots, rows_padded, nctr;
+  // small-batch path (select.cu): one row block, scores dumped [Q][small_ld] + per-range lists
+  bool small; int64_t small_ld; int splits; size_t scores_bytes, extra_bytes;
+};
+constexpr size_t kSmallScoreBytesMax = 64u << 20;   // the dump must stay L2 resident
 ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int dtype, int sm) {
   ScanLayout L{};
   L.tc = use_tc(dtype);
@@ -95,6 +100,15 @@ ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int dtype, int sm) {
     L.nslots = plan_nslots(L.plan);
     L.rows_padded = L.plan.ru * L.plan.cs;
     L.nctr = plan_nctr(L.plan);
+    L.small_ld = (V + kChunk - 1) / kChunk * kChunk;
+    L.scores_bytes = (((size_t)Q * L.small_ld * sizeof(float)) + 255) & ~(size_t)255;
+    L.small = num_rb == 1 && L.scores_bytes <= kSmallScoreBytesMax && !g_opt_nosmall.load();
+    if (L.small) {
+      L.splits = select_splits(V);
+      // lists sized for k = MCL_MAX_K: the workspace query does not depend on k
+      L.extra_bytes = L.scores_bytes + ((((size_t)L.splits * Q * MCL_MAX_K * 4) + 255) & ~(size_t)255) +
+                      (size_t)L.splits * Q * MCL_MAX_K * 8;
+    }
   } else {
     L.nsplit = simt_nsplit(Q, V, sm);
     L.nslots = num_rb * L.nsplit;
@@ -137,13 +151,17 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   if ((rc = require_sm100(&di))) return rc;
   if (Q == 0) return MCL_OK;
   const ScanLayout L = scan_layout(Q, V, D, dtype, di.sm);
-  Workspace ws = carve_workspace(workspace, L.nslots, L.rows_padded, L.nctr);
+  Workspace ws = carve_workspace(workspace, L.nslots, L.rows_padded, L.nctr, L.extra_bytes);
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
              g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap,
-             (int)g_opt_l2.load()};
+             (int)g_opt_l2.load(), nullptr, 0};
+  // Small batches (one row block) without a caller-side score dump: the scan keeps only the
+  // statistics and drops the scores into the workspace; select.cu picks the top-k from them.
+  const bool small = L.small && !dbg;
+  if (small) { a.small_scores = (float*)ws.extra; a.small_ld = L.small_ld; }
   SlotMap map{};
   cudaError_t e;
   const bool phases = g_opt_phase.load() != 0;
@@ -168,9 +186,19 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   }
   g_launches++;
   if (phases) cudaEventRecord(ev[2], stream);
-  e = launch_merge_slots(ws.sv, map, Q, k, inv_q, scale, softcap, index_base, topk_val, topk_idx, row_stats, stream);
-  if (e != cudaSuccess) return cuda_fail(e, "merge launch");
-  g_launches++;
+  if (small) {
+    char* lists = (char*)ws.extra + L.scores_bytes;
+    float* list_val = (float*)lists;
+    int64_t* list_idx = (int64_t*)(lists + ((((size_t)L.splits * Q * MCL_MAX_K * 4) + 255) & ~(size_t)255));
+    e = launch_select_small(a.small_scores, L.small_ld, V, Q, k, ws.sv, map, list_val, list_idx, ws.tau_shared, index_base,
+                            topk_val, topk_idx, row_stats, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "select launch");
+    g_launches++;
+  } else {
+    e = launch_merge_slots(ws.sv, map, Q, k, inv_q, scale, softcap, index_base, topk_val, topk_idx, row_stats, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "merge launch");
+    g_launches++;
+  }
   if (phases) {   // debug only: synchronises
     cudaEventRecord(ev[3], stream);
     cudaEventSynchronize(ev[3]);
@@ -297,7 +325,7 @@ size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, in
   if (!dev_info(&di)) { cudaGetLastError(); di.sm = 148; }
   if (Q <= 0 || V_local <= 0 || D <= 0) return 256;
   const ScanLayout L = scan_layout(Q, V_local, D, dtype, di.sm);
-  return carve_workspace(nullptr, L.nslots, L.rows_padded, L.nctr).bytes;
+  return carve_workspace(nullptr, L.nslots, L.rows_padded, L.nctr, L.extra_bytes).bytes;
 }
 
 int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
@@ -506,6 +534,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 8) return g_opt_segpen.exchange(value);
   if (opt == 9) return g_opt_l2.exchange(value);
   if (opt == 10) return g_opt_win.exchange(value);
+  if (opt == 11) return g_opt_nosmall.exchange(value);
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }

@@ -11,9 +11,12 @@ namespace mcl {
 constexpr int kBlockM = 128;        // query rows per CTA tile  (UMMA M, TMEM lanes)
 constexpr int kBlockN = 256;        // table rows per tile      (UMMA N, TMEM columns)
 constexpr int kBlockK = 64;         // bf16 per K slice = 128 B = one SWIZZLE_128B row
+// 160 = k_max (64) + slack + room for three more chunks of appends: measured against 128 / 192 /
+// 256 on B200 (profiles/): fewer compactions than 128 without the L2 footprint of 192+.
 #ifndef MCL_CAND_CAP
-#define MCL_CAND_CAP 128
+#define MCL_CAND_CAP 160
 #endif
+static_assert(MCL_CAND_CAP % 32 == 0 && MCL_CAND_CAP >= 128, "candidate buffer: whole warps of entries, >= k_max + slack + 2 chunks");
 constexpr int kCandCap = MCL_CAND_CAP;  // candidate-buffer entries per query row and slot
 constexpr int kChunk = 32;          // score columns one tcgen05.ld hands a thread
 constexpr float kLog2e = 1.4426950408889634f;

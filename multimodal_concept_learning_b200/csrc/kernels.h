@@ -24,6 +24,8 @@ struct ScanArgs {
   void* sync_ctr;            // [plan_nctr] int zeroed before launch (tcgen05 scan)
   float softcap;             // 0 = off; c > 0: logits are c*tanh(z/c)
   int l2_mode;               // bit 0: query tiles evict-last, bit 1: table tiles evict-first
+  float* small_scores;       // small-batch path: [Q][small_ld] score dump, top-k filter off (nullable)
+  int64_t small_ld;
 };
 
 // Tile plan of the tcgen05 scan (plan.h).  ctas / gu / cluster = 0: heuristic.  leftover = 0
@@ -41,11 +43,12 @@ struct Workspace {
   void* sync_ctr;     // window-arrival counters of the tile scheduler (follow tau_shared)
   size_t zero_bytes;  // tau_shared + sync_ctr: cleared before every scan
   SlotView sv;
+  void* extra;        // path-specific tail (small-batch path: score dump + per-range lists)
   int nslots;
   size_t bytes;
 };
 // carve `nslots` slots out of a caller buffer (base may be null to only size it)
-Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr);
+Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t extra_bytes);
 
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen);
@@ -59,6 +62,13 @@ cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q
                                const float* inv_q, float scale, float softcap, int64_t index_base,
                                float* topk_val, int64_t* topk_idx, float* row_stats,
                                cudaStream_t s);
+// Small-batch path (select.cu): exact top-k of the dumped scores [Q][ld] + the slots' statistics.
+// list_val / list_idx: [select_splits(V)][Q][k] scratch.
+int select_splits(int64_t V);
+cudaError_t launch_select_small(const float* scores, int64_t ld, int64_t V, int64_t Q, int k,
+                                const SlotView& sv, const SlotMap& map, float* list_val,
+                                int64_t* list_idx, void* row_ctr, int64_t index_base, float* topk_val,
+                                int64_t* topk_idx, float* row_stats, cudaStream_t s);
 // R per-shard results (rank r's arrays start r * stride bytes after the base) -> final
 cudaError_t launch_merge_ranks(const float* val, const int64_t* idx, const float* stats,
                                size_t val_stride, size_t idx_stride, size_t stats_stride, int R,

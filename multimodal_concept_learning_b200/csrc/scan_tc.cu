@@ -56,6 +56,8 @@ struct TcParams {
   int* sync_ctr;                // [plan_nctr] CTAs that started a window, zeroed
   float softcap;                // 0 = off; c > 0: logits are c*tanh(z/c) (kCap instantiation)
   unsigned long long pol_q, pol_t;   // L2 eviction priority of the query / table tile loads
+  float* small_scores;          // small-batch path (select.cu): [Q][small_ld] scores, top-k filter off
+  int small_ld;
 };
 
 // kCS = CTAs per cluster.  kCS = 1: every CTA multiplies its own 128 x 256 tile
@@ -232,7 +234,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       st.reset(slot_buf + (size_t)row_in_tile * kCandCap);
       warp_buf = slot_buf + (size_t)(quarter * 32) * kCandCap;
       row = (long long)rb * kBlockM + row_in_tile;
-      if (row >= p.Q) st.tau = INFINITY;                // padding rows never append / compact
+      if (row >= p.Q || p.small_scores) st.tau = INFINITY;   // padding rows (and the small-batch path) never append
       rs = ((row < p.Q && p.inv_q) ? p.inv_q[row] : 1.f) * p.scale;
       a = (kCap ? p.softcap : rs) * kLog2e;
       const float rc = kCap ? rs / p.softcap : 0.f;
@@ -293,6 +295,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 p.dbg_scores[(size_t)row * p.V + col0 + i] =
                     kCap ? p.softcap * tanhf(y[i] * rc) : y[i] * rs;
           }
+          if (p.small_scores && row < p.Q) {             // 128 B per row and chunk, -inf past the table's end
+            float4* dst = reinterpret_cast<float4*>(p.small_scores + (size_t)row * p.small_ld + col0);
+#pragma unroll
+            for (int i = 0; i < kChunk / 4; ++i) {
+              float z[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float v = kCap ? p.softcap * tanhf(y[4 * i + j] * rc) : y[4 * i + j] * rs;
+                z[j] = (4 * i + j < n_valid) ? v : -INFINITY;
+              }
+              dst[i] = make_float4(z[0], z[1], z[2], z[3]);
+            }
+          }
           if (n_valid == kChunk) row_process_chunk<false, kCap>(st, y, col0, kChunk, a, lab_local, rc);
           else row_process_chunk<true, kCap>(st, y, col0, n_valid, a, lab_local, rc);
           __syncwarp();
@@ -322,14 +337,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
   }
 
-  if (p.timing && threadIdx.x == 0) {
+  tc_fence_before();
+  __syncthreads();
+  if (p.timing && threadIdx.x == 0) {   // after the barrier: the epilogue warps are done too
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     p.timing[2 * blockIdx.x] = t_start;
     p.timing[2 * blockIdx.x + 1] = t1;
   }
-  tc_fence_before();
-  __syncthreads();
   if (kCS > 1) cluster_sync_all();      // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -502,7 +517,7 @@ TcPlan make_tc_plan(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKno
   return e.p;
 }
 
-Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
+Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t extra_bytes) {
   Workspace w{};
   w.nslots = nslots;
   size_t off = 0;
@@ -513,6 +528,7 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
   const size_t o_cand = take((size_t)nslots * kBlockM * kCandCap * sizeof(uint2));
   const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int2));
   const size_t o_stats = take((size_t)nslots * kBlockM * sizeof(float4));
+  const size_t o_extra = take(extra_bytes);
   w.bytes = off;
   w.zero_bytes = o_ctr + (((size_t)nctr * sizeof(int) + 255) & ~(size_t)255) - o_tau;
   if (base) {
@@ -523,6 +539,7 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr) {
     w.sv.cand = (uint2*)(b + o_cand);
     w.sv.cnt = (int2*)(b + o_cnt);
     w.sv.stats = (float4*)(b + o_stats);
+    w.extra = (void*)(b + o_extra);
   }
   return w;
 }
@@ -605,6 +622,7 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
   p.tau_shared = (uint32_t*)a.tau_shared;
   p.sync_ctr = (int*)a.sync_ctr;
   p.softcap = a.softcap;
+  p.small_scores = a.small_scores; p.small_ld = (int)a.small_ld;
   p.pol_q = (a.l2_mode & 1) ? kL2EvictLast : kL2EvictNormal;
   p.pol_t = (a.l2_mode & 2) ? kL2EvictFirst : ((a.l2_mode & 4) ? kL2EvictLast : kL2EvictNormal);
   const bool cap = a.softcap > 0.f;

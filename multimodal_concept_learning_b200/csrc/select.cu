@@ -1,0 +1,233 @@
+// Small query batches (Q <= 128: one row block -- the reference's own workloads score 6-96
+// concept tokens against the vocabulary, token_embedding_analysis.py:183-260).
+//
+// With one row block the table read bounds the scan (AI ~ Q flop/B) and every CTA sees only a
+// tile or two, so the streaming top-k filter of the big-batch path never leaves its start-up
+// transient (threshold -inf: every score is a candidate, buffers compact three times per tile).
+// Here the scan kernel's epilogue keeps only the log-sum-exp statistics and drops the scores
+// -- Q*V*4 bytes, at most a few percent of the table bytes, L2 resident -- into the workspace;
+// the rows' top-k come from an exact radix selection over them:
+//   row_select_kernel   one CTA per (row, range of kSelectCols columns): 64-bit keys
+//                       (value key, ~column) in registers; the k-th largest of the 256 thread
+//                       maxima bounds the k-th largest key from below, the ~k keys that survive
+//                       it are sorted in shared memory (an exact radix select stands by for
+//                       adversarial data) -> a sorted list per range; the last range CTA of a
+//                       row folds the lists and the slots' (m, s, sum_z, z_label)
+// Same tie rule (value desc, table row asc) and the same output values as the slot merge.
+#include <atomic>
+#include "kernels.h"
+#include "toplist.cuh"
+
+namespace mcl {
+
+constexpr int kSelectThreads = 256;
+constexpr int kSelectE = 24;                                   // keys per thread
+constexpr int kSelectCols = kSelectThreads * kSelectE;          // 6144 columns per CTA
+constexpr int kLiveCap = 1024;                                  // shared-memory list of live keys
+
+int select_splits(int64_t V) { return (int)((V + kSelectCols - 1) / kSelectCols); }
+
+// Descending bitonic sort of a[0 .. n) (n a power of two) by the whole block.
+__device__ __forceinline__ void block_sort_desc(unsigned long long* a, int n, int tid) {
+  for (int size = 2; size <= n; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < (n >> 1); i += kSelectThreads) {
+        const int lo = ((i / stride) * stride << 1) + (i % stride), hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  __syncthreads();
+}
+
+// One warp folds the R sorted lists of `row` and the slots' statistics into the final outputs.
+__device__ __forceinline__ void finish_row(const SlotView& sv, const SlotMap& map, const float* list_val,
+                                           const long long* list_idx, int splits, int Q, int k, int row,
+                                           long long index_base, float* topk_val, long long* topk_idx,
+                                           float4* row_stats, int lane) {
+  const int rb = row / kBlockM, r_in = row % kBlockM;
+  const int slot0 = rb * map.stride, nsplit = slotmap_count(map, rb);
+  // (m, s, sum_z, z_label) over the row's slots: one pass of independent loads per lane, merged
+  // as (max, rescaled sum) pairs
+  float m = -INFINITY, s = 0.f, sum_z = 0.f, z_label = 0.f;
+  for (int i = lane; i < nsplit; i += 32) {
+    const float4 st = __ldcg(&sv.stats[(size_t)(slot0 + i) * kBlockM + r_in]);
+    const float mn = fmaxf(m, st.x);
+    s = (s > 0.f ? s * expf(m - mn) : 0.f) + (st.y > 0.f ? st.y * expf(st.x - mn) : 0.f);
+    m = mn;
+    sum_z += st.z;
+    z_label += st.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, m2);
+    s = (s > 0.f ? s * expf(m - mn) : 0.f) + (s2 > 0.f ? s2 * expf(m2 - mn) : 0.f);
+    m = mn;
+    sum_z += __shfl_xor_sync(0xffffffffu, sum_z, o);
+    z_label += __shfl_xor_sync(0xffffffffu, z_label, o);
+  }
+  if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
+  TopList top; top.init();
+  for (int sp = 0; sp < splits; ++sp) {
+    const float* v = list_val + ((size_t)sp * Q + row) * k;
+    const long long* ix = list_idx + ((size_t)sp * Q + row) * k;
+    uint64_t b0 = 0ull, b1 = 0ull;
+    if (lane < k) { const long long j = __ldcg(ix + lane); if (j >= 0) b0 = pack_key(__ldcg(v + lane), (uint32_t)j); }
+    if (lane + 32 < k) { const long long j = __ldcg(ix + lane + 32); if (j >= 0) b1 = pack_key(__ldcg(v + lane + 32), (uint32_t)j); }
+    top.push_sorted(b0, b1, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int p = i * 32 + lane;
+    const uint64_t key = i ? top.r1 : top.r0;
+    if (p < k) {
+      const bool empty = (key == 0ull);
+      topk_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32));
+      topk_idx[(size_t)row * k + p] = empty ? -1ll : index_base + (long long)(uint32_t)(~(uint32_t)key);
+    }
+  }
+}
+
+// grid (ranges, Q).  The last range CTA of a row to finish (a counter per row in the cleared
+// threshold words, which this path does not otherwise use) also folds the row's lists.
+__global__ void __launch_bounds__(kSelectThreads)
+row_select_kernel(const float* __restrict__ scores, int ld, int V, int Q, int k,
+                  float* __restrict__ list_val, long long* __restrict__ list_idx,
+                  unsigned* __restrict__ row_ctr, SlotView sv, const SlotMap map, long long index_base,
+                  float* __restrict__ topk_val, long long* __restrict__ topk_idx,
+                  float4* __restrict__ row_stats) {
+  __shared__ unsigned long long buf[kLiveCap];
+  __shared__ int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_kk, s_cnt, s_last;
+  const int split = blockIdx.x, splits = gridDim.x, row = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = split * kSelectCols;
+  const int n = max(0, min(kSelectCols, V - c0));            // valid columns of this range
+  const int k_eff = min(k, n);
+  const float* src = scores + (size_t)row * ld + c0;
+
+  unsigned long long key[kSelectE];
+  unsigned long long mx = 0ull;
+#pragma unroll
+  for (int e = 0; e < kSelectE; ++e) {
+    const int c = tid + e * kSelectThreads;                    // coalesced
+    key[e] = (c < n) ? pack_key(__ldcg(src + c), (uint32_t)(c0 + c)) : 0ull;   // valid keys are never 0
+    mx = max64(mx, key[e]);
+  }
+  // A lower bound of the k-th largest key: the k-th largest of the 256 thread maxima (k distinct
+  // keys at or above it exist).  On anything but adversarial data only ~k keys survive it.
+  buf[tid] = mx;
+  if (tid == 0) s_cnt = 0;
+  block_sort_desc(buf, kSelectThreads, tid);
+  const unsigned long long bound = k_eff > 0 ? buf[k_eff - 1] : ~0ull;   // 0 when n < 256: keep every key
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kSelectE; ++e)
+    if (key[e] != 0ull && key[e] >= bound) {
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < kLiveCap) buf[pos] = key[e];
+    }
+  __syncthreads();
+  const int live = s_cnt;
+  if (live <= kLiveCap) {
+    int P = 64;
+    while (P < live) P <<= 1;
+    for (int i = live + tid; i < P; i += kSelectThreads) buf[i] = 0ull;
+    block_sort_desc(buf, P, tid);                              // buf[0 .. k_eff) = the answer
+  } else {
+    // ---- fallback (the bound kept > 1024 keys): exact MSB-first radix select, one byte per pass
+    unsigned long long prefix = 0ull;
+    int kk = k_eff;
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      hist[tid] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < kSelectE; ++e) {
+        const bool lv = key[e] != 0ull && (pass == 0 || (key[e] >> (shift + 8)) == (prefix >> (shift + 8)));
+        const int bin = lv ? (int)((key[e] >> shift) & 255ull) : 256;
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);   // warp-aggregated atomics
+        if (lv && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int mine = 0;                                              // lane l owns bins 255-8l .. 248-8l
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += hist[255 - 8 * lane - j];
+        int above = mine;                                          // inclusive scan over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, above, o);
+          if (lane >= o) above += t;
+        }
+        const int before = above - mine;
+        if (before < kk && kk <= above) {
+          int cum = before, bin = 255 - 8 * lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int h = hist[255 - 8 * lane - j];
+            if (cum < kk && kk <= cum + h) { bin = 255 - 8 * lane - j; break; }
+            cum += h;
+          }
+          s_prefix = prefix | ((unsigned long long)bin << shift);
+          s_kk = kk - cum;
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      kk = s_kk;
+    }
+    if (tid == 0) s_cnt = 0;
+    if (tid < 64) buf[tid] = 0ull;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kSelectE; ++e)
+      if (key[e] != 0ull && key[e] >= prefix) {                    // exactly k_eff keys (they are unique)
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < 64) buf[pos] = key[e];
+      }
+    __syncthreads();
+    block_sort_desc(buf, 64, tid);
+  }
+  if (tid < k) {
+    const unsigned long long kv = tid < k_eff ? buf[tid] : 0ull;
+    const bool empty = (kv == 0ull);
+    list_val[((size_t)split * Q + row) * k + tid] = empty ? -INFINITY : key2f((uint32_t)(kv >> 32));
+    list_idx[((size_t)split * Q + row) * k + tid] = empty ? -1ll : (long long)(uint32_t)(~(uint32_t)kv);
+  }
+  // last range of the row: fold the lists
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(row_ctr + row, 1u) == (unsigned)(splits - 1));
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    finish_row(sv, map, list_val, list_idx, splits, Q, k, row, index_base, topk_val, topk_idx, row_stats, lane);
+  }
+}
+
+cudaError_t launch_select_small(const float* scores, int64_t ld, int64_t V, int64_t Q, int k,
+                                const SlotView& sv, const SlotMap& map, float* list_val,
+                                int64_t* list_idx, void* row_ctr, int64_t index_base, float* topk_val,
+                                int64_t* topk_idx, float* row_stats, cudaStream_t s) {
+  if (Q == 0) return cudaSuccess;
+  // same shared-memory carve-out as the scan kernel this follows (see launch_merge_slots)
+  static std::atomic<bool> pref_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !pref_set[dev].load()) {
+    cudaFuncSetAttribute(row_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    pref_set[dev].store(true);
+  }
+  row_select_kernel<<<dim3((unsigned)select_splits(V), (unsigned)Q), kSelectThreads, 0, s>>>(
+      scores, (int)ld, (int)V, (int)Q, k, list_val, (long long*)list_idx, (unsigned*)row_ctr, sv, map,
+      (long long)index_base, topk_val, (long long*)topk_idx, (float4*)row_stats);
+  return cudaGetLastError();
+}
+
+}  // namespace mcl

@@ -334,3 +334,47 @@ def test_graphed_scan_equals_direct_scan(mcl, Q, with_labels):
         check_topk(out.topk_val, out.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-4)
         if with_labels:
             torch.testing.assert_close(out.loss.cpu().double(), ref.loss.double(), rtol=RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("Q,V,D,k", [(16, 50257, 768, 50), (96, 20000, 1152, 64), (128, 6144, 64, 50),
+                                     (5, 6145, 72, 7), (1, 300, 8, 1)])
+def test_small_batch_path_equals_streaming_path(mcl, Q, V, D, k):
+    """One-row-block batches take the score-dump + radix-select path (select.cu); option 11
+    sends them through the streaming top-k filter instead.  Same scores, same tie rule: the
+    outputs must be bit-identical, and match the oracle."""
+    q, t = make_inputs(Q, V, D, 70 + Q)
+    t[V // 2] = t[3]                                   # an exact duplicate: the lower row must win
+    labels = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(Q))
+    qd, td = q.cuda(), t.cuda()
+    a = mcl.concept_scan(qd, td, k, scale=25.0, labels=labels, label_smoothing=0.1)
+    old = mcl.set_option(11, 1)
+    try:
+        b = mcl.concept_scan(qd, td, k, scale=25.0, labels=labels, label_smoothing=0.1)
+    finally:
+        mcl.set_option(11, old)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+    torch.testing.assert_close(a.stats, b.stats, rtol=1e-6, atol=1e-6)
+    if Q * V <= 2_000_000:
+        ref = R.concept_scan_ref(q, t, k, scale=25.0, labels=labels, label_smoothing=0.1, keep_scores=True)
+        check_topk(a.topk_val, a.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-4)
+        check_stats(a.stats, ref, rtol=RTOL, atol=1e-3)
+
+
+def test_small_batch_selection_fallback_and_ties(mcl):
+    """Adversarial layout for the selection kernel's thread-maxima bound: 56 of the 256 column
+    classes (mod 256) hold all the large scores, so the bound keeps > 1024 keys and the exact
+    radix select runs; large scores repeat across classes, so the top-k is decided by the
+    lowest-row tie rule.  Raw dot products of bf16-exact integers: the expected answer is exact."""
+    V, D, k = 3 * 6144 + 77, 16, 64
+    j = torch.arange(V)
+    val = torch.where((j % 256) < 56, 100.0 + (j // 256).float(), (j % 5).float())   # < 256: exact in bf16
+    t = torch.zeros(V, D)
+    t[:, 0] = val
+    q = torch.zeros(3, D)
+    q[:, 0] = torch.tensor([1.0, 2.0, -1.0])
+    out = mcl.concept_scan(q.bfloat16().cuda(), t.bfloat16().cuda(), k, normalize_q=False, normalize_t=False)
+    for r, mult in enumerate([1.0, 2.0, -1.0]):
+        sc = (val * mult).double()
+        order = sorted(range(V), key=lambda c: (-sc[c].item(), c))[:k]
+        assert out.topk_idx[r].cpu().tolist() == order, f"row {r}"
+        torch.testing.assert_close(out.topk_val[r].cpu().double(), sc[order], rtol=0, atol=0)
