@@ -175,6 +175,13 @@ def run_workload(name, steps, warmup, world, rank, device, with_e2e=True, sample
     clocks = sampler.stop() if sampler else None
     res = {"ms_per_step": ms / steps, "value": w["Q"] * steps / (ms * 1e-3), "gpu_launches": int(launches),
            "clocks": clocks}
+    if world == 1 and w["Q"] <= 128:
+        # launch-bound regime: the same step replayed from a CUDA graph (public API GraphedConceptScan)
+        g = mcl.GraphedConceptScan(table, K_TOP, w["Q"], normalize=w["normalize"], scale=w["scale"],
+                                   inv_norm_t=step.inv_t, with_labels=labels is not None)
+        gms = time_steps(lambda: g(q, labels), steps, warmup, world, device)
+        res["graphed_ms_per_step"] = gms / steps
+        del g
     flops = 2.0 * w["Q"] * w["V"] * w["D"]
     res["tflops"] = flops / (ms / steps * 1e-3) / 1e12
     res["alg_bytes"] = 2.0 * (w["V"] * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * K_TOP + 16)
@@ -310,9 +317,9 @@ def main():
     out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                        "frac": achieved / pk["bf16_tflops"], "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],
                        "peak_source": pk["source"] + " (burst cuBLAS bf16)",
-                       # dram__bytes_read.sum + dram__bytes_write.sum of scan_tc_kernel<2>, one launch of this
-                       # workload at N=1, from profiles/r01_c3_scan_tc_v6_ncu_raw.csv (ncu --set full)
-                       "traffic": 3.887e9 if (args.workload == "c3" and world == 1) else None,
+                       # dram__bytes_read.sum + dram__bytes_write.sum of scan_tc_kernel<2,0>, one launch of this
+                       # workload at N=1, from profiles/r01_c3_scan_tc_v8_ncu_raw.csv (ncu --set full)
+                       "traffic": 5.665e9 if (args.workload == "c3" and world == 1) else None,
                        "traffic_unit": "bytes per launch (algorithmic: %.3e)" % (
                            2.0 * (w["V"] / world * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * K_TOP + 16)),
                        "kernel": "scan_tc_kernel (per GPU; step time includes the merge kernel)"}
@@ -330,10 +337,16 @@ def main():
                     r = run_workload(name, max(3, args.steps // 4), 3, 1, 0, device, with_e2e=False)
                     ww = WORKLOADS[name]
                     hbm = r["alg_bytes"] / (r["ms_per_step"] * 1e-3) / 1e9
-                    sweep.append({"workload": name, "Q": ww["Q"], "V": ww["V"], "D": ww["D"],
-                                  "value": r["value"], "ms_per_step": r["ms_per_step"], "tflops": r["tflops"],
-                                  "tensor_frac": r["tflops"] / pk["bf16_tflops"], "hbm_gbs": hbm,
-                                  "hbm_frac": hbm / pk["hbm_gbs"]})
+                    entry = {"workload": name, "Q": ww["Q"], "V": ww["V"], "D": ww["D"],
+                             "value": r["value"], "ms_per_step": r["ms_per_step"], "tflops": r["tflops"],
+                             "tensor_frac": r["tflops"] / pk["bf16_tflops"], "hbm_gbs": hbm,
+                             "hbm_frac": hbm / pk["hbm_gbs"]}
+                    if "graphed_ms_per_step" in r:      # small batches: CUDA-graph replay of the same step
+                        gh = r["alg_bytes"] / (r["graphed_ms_per_step"] * 1e-3) / 1e9
+                        entry["graphed"] = {"ms_per_step": r["graphed_ms_per_step"],
+                                            "value": ww["Q"] / (r["graphed_ms_per_step"] * 1e-3),
+                                            "hbm_gbs": gh, "hbm_frac": gh / pk["hbm_gbs"]}
+                    sweep.append(entry)
                 except Exception as e:   # a secondary workload must not void the headline
                     sweep.append({"workload": name, "error": f"{type(e).__name__}: {e}"[:200]})
             out["sweep"] = sweep

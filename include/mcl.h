@@ -168,6 +168,14 @@ int mcl_comm_unique_id(void* unique_id_out /*host, 128 B*/);
 int mcl_comm_init(const void* unique_id /*host, 128 B*/, int world, int rank, void** comm_out);
 int mcl_comm_destroy(void* comm);
 
+/*
+ * Plain all-gather over the library's communicator on `stream` (in place when
+ * send == recv + rank * bytes_per_rank).  The host layer uses it to assemble a replicated query
+ * batch from the 1/N slices each rank uploaded over its own PCIe link.
+ */
+int mcl_comm_all_gather(void* comm, const void* send, void* recv, size_t bytes_per_rank,
+                        mcl_stream_t stream);
+
 /* bytes of `gather_buf` needed by mcl_concept_scan_sharded */
 size_t mcl_sharded_gather_bytes(int64_t Q, int k, int world);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mcl_comm_unique_id": (_i32, [_ptr]),
     "mcl_comm_init": (_i32, [_ptr, _i32, _i32, C.POINTER(_ptr)]),
     "mcl_comm_destroy": (_i32, [_ptr]),
+    "mcl_comm_all_gather": (_i32, [_ptr, _ptr, _ptr, _sz, _ptr]),
     "mcl_sharded_gather_bytes": (_sz, [_i64, _i32, _i32]),
     "mcl_concept_scan_sharded": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
                                         _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr,

@@ -427,6 +427,17 @@ int mcl_comm_destroy(void* comm) {
   return MCL_OK;
 }
 
+int mcl_comm_all_gather(void* comm, const void* send, void* recv, size_t bytes_per_rank,
+                        mcl_stream_t stream) {
+  NcclApi* n = nccl();
+  if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable");
+  if (!comm || !send || !recv) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  if (bytes_per_rank == 0) return MCL_OK;
+  const int rc = n->allgather(send, recv, bytes_per_rank, /*ncclInt8*/ 0, comm, (cudaStream_t)stream);
+  if (rc) return nccl_fail(n, rc, "ncclAllGather");
+  return MCL_OK;
+}
+
 size_t mcl_sharded_gather_bytes(int64_t Q, int k, int world) {
   if (Q < 0 || k < 1 || world < 1) return 0;
   // R full records (all-gather path) + room for R mini-records of Q/R rows (row-exchange path)

@@ -52,13 +52,22 @@ __device__ __forceinline__ void finish_row(const SlotView& sv, const SlotMap& ma
   // (m, s, sum_z, z_label) over the row's slots: one pass of independent loads per lane, merged
   // as (max, rescaled sum) pairs
   float m = -INFINITY, s = 0.f, sum_z = 0.f, z_label = 0.f;
-  for (int i = lane; i < nsplit; i += 32) {
-    const float4 st = __ldcg(&sv.stats[(size_t)(slot0 + i) * kBlockM + r_in]);
-    const float mn = fmaxf(m, st.x);
-    s = (s > 0.f ? s * expf(m - mn) : 0.f) + (st.y > 0.f ? st.y * expf(st.x - mn) : 0.f);
-    m = mn;
-    sum_z += st.z;
-    z_label += st.w;
+  for (int base = 0; base < nsplit; base += 256) {
+    float4 st[8];                                   // eight independent loads in flight per lane
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = base + lane + 32 * j;
+      st[j] = i < nsplit ? __ldcg(&sv.stats[(size_t)(slot0 + i) * kBlockM + r_in])
+                         : make_float4(-INFINITY, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mn = fmaxf(m, st[j].x);
+      s = (s > 0.f ? s * expf(m - mn) : 0.f) + (st[j].y > 0.f ? st[j].y * expf(st[j].x - mn) : 0.f);
+      m = mn;
+      sum_z += st[j].z;
+      z_label += st[j].w;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -71,12 +80,19 @@ __device__ __forceinline__ void finish_row(const SlotView& sv, const SlotMap& ma
   }
   if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
   TopList top; top.init();
-  for (int sp = 0; sp < splits; ++sp) {
+  auto load_list = [&](int sp, uint64_t& b0, uint64_t& b1) {
+    b0 = 0ull; b1 = 0ull;
+    if (sp >= splits) return;
     const float* v = list_val + ((size_t)sp * Q + row) * k;
     const long long* ix = list_idx + ((size_t)sp * Q + row) * k;
-    uint64_t b0 = 0ull, b1 = 0ull;
     if (lane < k) { const long long j = __ldcg(ix + lane); if (j >= 0) b0 = pack_key(__ldcg(v + lane), (uint32_t)j); }
     if (lane + 32 < k) { const long long j = __ldcg(ix + lane + 32); if (j >= 0) b1 = pack_key(__ldcg(v + lane + 32), (uint32_t)j); }
+  };
+  uint64_t n0, n1;
+  load_list(0, n0, n1);
+  for (int sp = 0; sp < splits; ++sp) {             // the next list's loads overlap this list's fold
+    const uint64_t b0 = n0, b1 = n1;
+    load_list(sp + 1, n0, n1);
     top.push_sorted(b0, b1, lane);
   }
 #pragma unroll

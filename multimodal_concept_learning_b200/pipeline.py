@@ -2,7 +2,8 @@
 i+1 and the device->host copy of result i-1 with the scan of batch i (two CUDA streams, two
 device buffers, events -- no host synchronisation inside the loop except on the result that is
 handed back).  This is the path a caller with queries in pinned host memory uses; `bench.py`
-measures its `e2e` number through it."""
+measures its `e2e` number through it.  With a sharded scanner every rank uploads 1/N of the batch and
+the ranks all-gather it over NVLink."""
 from __future__ import annotations
 
 from typing import Iterable, Iterator, Optional, Tuple
@@ -46,11 +47,13 @@ class HostQueryPipeline:
         if nxt is not None:
             staged = self._stage(nxt, slot, main)
         while staged is not None:
-            q_dev, ready = staged
+            q_dev, ready, sliced = staged
             nxt = next(it, None)
             slot ^= 1
             staged = self._stage(nxt, slot, main) if nxt is not None else None   # H2D of i+1
             main.wait_event(ready)
+            if sliced:                    # on the main stream: one communicator, one order of collectives
+                self.scanner.all_gather_rows(q_dev)
             out = self._scan(q_dev, labels)                                      # scan of i
             done = torch.cuda.Event()
             done.record(main)
@@ -77,8 +80,18 @@ class HostQueryPipeline:
             self._bufs[slot] = buf
         # the buffer may still be read by the scan two batches ago
         self.copy_stream.wait_stream(main)
+        world = getattr(self.scanner, "world", 1)
+        sliced = world > 1 and host_q.shape[0] % world == 0
         with torch.cuda.stream(self.copy_stream):
-            buf.copy_(host_q, non_blocking=True)
+            if sliced:
+                # Sharded scan: every rank needs the whole batch.  Each rank uploads only its 1/N
+                # row slice over its own PCIe link; `run` all-gathers the slices over NVLink
+                # right before the scan, instead of N full copies competing for host bandwidth.
+                rows = host_q.shape[0] // world
+                r = self.scanner.rank
+                buf[r * rows:(r + 1) * rows].copy_(host_q[r * rows:(r + 1) * rows], non_blocking=True)
+            else:
+                buf.copy_(host_q, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return buf, ev
+        return buf, ev, sliced

@@ -93,6 +93,19 @@ class ShardedConceptScan:
         except Exception:
             pass
 
+    def all_gather_rows(self, buf: Tensor) -> None:
+        """In-place all-gather of ``buf [world*rows, ...]`` on torch's current stream: rank r
+        contributes rows ``[r*rows, (r+1)*rows)``.  Uses the library's own communicator, so it is
+        ordered with the scans' collectives on the same stream."""
+        if self.world == 1:
+            return
+        if not buf.is_contiguous() or buf.shape[0] % self.world:
+            raise ValueError("buffer must be contiguous with a row count divisible by the world size")
+        per = buf.numel() * buf.element_size() // self.world
+        with torch.cuda.device(self.device):
+            check(load().mcl_comm_all_gather(self._comm, buf.data_ptr() + self.rank * per, buf.data_ptr(), per,
+                                             ops._stream(self.device)))
+
     def scan(self, q: Tensor, k: int, *, normalize_q: bool = True, scale: float = 1.0,
              labels: Optional[Tensor] = None, label_smoothing: float = 0.0,
              inv_norm_q: Optional[Tensor] = None) -> ops.ScanOutput:

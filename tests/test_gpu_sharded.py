@@ -47,6 +47,15 @@ def _worker(rank, world, port, ret):
         assert torch.equal(out.topk_val, full.topk_val), "sharded values differ"
         torch.testing.assert_close(out.lse, full.lse, rtol=1e-6, atol=1e-5)
         torch.testing.assert_close(out.loss, full.loss, rtol=1e-6, atol=1e-6)
+        # host batches through the streaming pipeline: each rank uploads 1/world of the rows and
+        # the library all-gathers them (Q = 300 rows divides by 2 and 4)
+        from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
+        pipe = HostQueryPipeline(td[lo:hi], k, scale=20.0, scanner=sc)
+        qh = q.pin_memory()
+        got = list(pipe.run([qh, qh.flip(0).contiguous().pin_memory(), qh]))
+        assert len(got) == 3
+        assert torch.equal(got[0][1], full.topk_idx.cpu()) and torch.equal(got[2][0], full.topk_val.cpu())
+        assert torch.equal(got[1][1], full.topk_idx.cpu().flip(0)), "second (row-reversed) batch differs"
         sc.close()
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
