@@ -1,17 +1,20 @@
 // The product path: fused similarity scan on Blackwell tensor cores.
 //
 //   scores tile [128 queries x 256 table rows] = Q_tile (bf16, K-major) * T_tile^T
-//   - operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 4-stage ring,
-//   - multiplied by tcgen05.mma (kind::f16, M128 N256 K16) issued by ONE thread,
+//   - operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into an mbarrier ring of
+//     192 KB (6 stages per CTA of a pair, 4 for a single CTA),
+//   - multiplied by tcgen05.mma (kind::f16, K16; M256 N256 issued by ONE thread for a CTA pair,
+//     M128 N256 for a single CTA),
 //   - accumulated in TMEM (2 x 256 fp32 columns, double buffered),
-//   - drained by four epilogue warps with tcgen05.ld: thread = query row = TMEM lane, so the
+//   - drained by eight epilogue warps with tcgen05.ld: thread = query row = TMEM lane, so the
 //     online log-sum-exp, running sum, label pick-up and top-k filter are thread-private
 //     (rowstate.cuh) and the [Q x V] score matrix never leaves the SM.
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue.  A warp may only read the TMEM lane quarter warp_id % 4, so two warps
 // share each quarter and split the tile's 256 columns in halves (own row state, own slot):
-// two resident warps per scheduler hide each other's latencies.
+// two resident warps per scheduler hide each other's latencies.  (Separate top-k and LSE warps,
+// 16 in all, were measured and are no faster: profiles/README.md.)
 //
 // Scheduling (plan.h): persistent workers (a worker = one CTA, or a CTA pair sharing one
 // cta_group::2 MMA).  Row units are taken in waves of gu; inside a wave the workers form nfull

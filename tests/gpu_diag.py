@@ -236,7 +236,7 @@ def stage_sched():
         times, plan = concept_scan_cta_times(q, t, 50, inv_norm_q=inv_q, inv_norm_t=inv_t)
         dur = (times[:, 1] - times[:, 0]).double() / 1e3
         span = float(times[:, 1].max() - times[:, 0].min()) / 1e3
-        print(f"[sched {name}] heuristic g={plan['g']} ng={plan['ng']} rounds={plan['rounds']} tpc={plan['tpc']}: {ms:.3f} ms "
+        print(f"[sched {name}] heuristic gu={plan['gu']} waves={plan['waves']} workers={plan['workers']} S={plan['S']}: {ms:.3f} ms "
               f"({2.0*Q*V*D/ms/1e9:.0f} TF/s); CTA busy us min/mean/max = {float(dur.min()):.0f}/{float(dur.mean()):.0f}/{float(dur.max()):.0f}, span {span:.0f}")
         gs = {"c3": [8, 16, 21, 32, 64], "c3/8": [8, 16, 32, 64], "c4": [37, 49, 74, 148], "c5": [18, 37, 74],
               "c2": [4, 8, 16, 32], "c1": [1]}[name]
