@@ -199,7 +199,9 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
  * segment of a tail worker (default 1), 9 = L2 eviction priority of the TMA loads (bit 0: query
  * tiles evict-last, bit 1: table tiles evict-first), 10 = drift window in tiles (0 = heuristic),
  * 11 = 1 sends one-row-block batches through the streaming top-k path instead of the score-dump +
- * radix-select path (tests, A/B); opt 100..102 read the last memset / scan / merge
+ * radix-select path (tests, A/B), 12 = 1 turns the joint threshold of a row's slots on (rowstate.cuh; measured: +3 % on C2,
+ * -3..-6 % elsewhere, so off by default);
+ * opt 100..102 read the last memset / scan / merge
  * time in ns.  Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);

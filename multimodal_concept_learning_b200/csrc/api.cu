@@ -17,7 +17,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
-std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0};
+std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0}, g_opt_joint{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
@@ -156,7 +156,8 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
-             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr, softcap,
+             g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr,
+             g_opt_joint.load() ? ws.joint : nullptr, softcap,
              (int)g_opt_l2.load(), nullptr, 0};
   // Small batches (one row block) without a caller-side score dump: the scan keeps only the
   // statistics and drops the scores into the workspace; select.cu picks the top-k from them.
@@ -546,6 +547,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 9) return g_opt_l2.exchange(value);
   if (opt == 10) return g_opt_win.exchange(value);
   if (opt == 11) return g_opt_nosmall.exchange(value);
+  if (opt == 12) return g_opt_joint.exchange(value);
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }

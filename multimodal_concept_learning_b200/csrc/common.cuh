@@ -140,6 +140,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
       "DONEB_%=:\n\t}\n" ::"r"(bar), "r"(parity), "r"(1000u)
       : "memory");
 }
+__device__ __forceinline__ uint4 ld_cg_v4_pinned(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 // ld.global.cg that stays where it is written (a plain __ldcg may be sunk to its use)
 __device__ __forceinline__ uint32_t ld_cg_u32_pinned(const uint32_t* p) {
   uint32_t v;

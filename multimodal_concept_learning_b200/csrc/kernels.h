@@ -22,6 +22,7 @@ struct ScanArgs {
   void* timing;              // nullable, [grid][2] uint64 (tcgen05 scan only)
   void* tau_shared;          // nullable, [num_rb*128] uint32 zeroed before launch (tcgen05 scan)
   void* sync_ctr;            // [plan_nctr] int zeroed before launch (tcgen05 scan)
+  void* joint;               // [padded rows][kJointWords] uint32 zeroed before launch (nullable: off)
   float softcap;             // 0 = off; c > 0: logits are c*tanh(z/c)
   int l2_mode;               // bit 0: query tiles evict-last, bit 1: table tiles evict-first
   float* small_scores;       // small-batch path: [Q][small_ld] score dump, top-k filter off (nullable)
@@ -41,7 +42,8 @@ struct Workspace {
   void* timing;   // [1024][2] uint64 at offset 0: per-CTA globaltimer start/end (debug option 3)
   void* tau_shared;   // one threshold word per (padded) query row, shared between CTAs
   void* sync_ctr;     // window-arrival counters of the tile scheduler (follow tau_shared)
-  size_t zero_bytes;  // tau_shared + sync_ctr: cleared before every scan
+  void* joint;        // joint-threshold words (follow sync_ctr)
+  size_t zero_bytes;  // tau_shared + sync_ctr + joint: cleared before every scan
   SlotView sv;
   void* extra;        // path-specific tail (small-batch path: score dump + per-range lists)
   int nslots;

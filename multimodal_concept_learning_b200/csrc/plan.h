@@ -33,6 +33,7 @@
 namespace mcl {
 
 constexpr int kMaxNodes = 4;
+constexpr int kJointWords = 8;   // joint-threshold words per query row (see rowstate.cuh)
 
 struct Node {
   int r0, R;       // row units [r0, r0 + R) of the wave
@@ -66,6 +67,8 @@ struct Seg {
   int j;         // slot of the row unit this segment ends in
   int sync;      // first drift counter of this segment's group or tail pass
   int members;   // CTAs walking these tiles side by side
+  int ng2;       // joint threshold: words in use for this wave's rows (0 = off)
+  int jw;        // joint threshold: word this segment's column half 0 publishes to (-1 = reads only)
 };
 
 MCL_HD const Chain& plan_chain(const TcPlan& p, int wave) {
@@ -88,13 +91,21 @@ MCL_HD bool seg_iter_next(const TcPlan& p, SegIter& it, Seg& s) {
     const int ng = nd.nfull * nd.R;
     const int u0 = it.v * p.gu + nd.r0;
     const int c0 = it.v * p.nsync + nd.sync0;
+    // joint threshold (rowstate.cuh): the column halves of the first groups of the wave's top node
+    // publish, every segment of the wave reads
+    int ng2 = 2 * ch.nd[0].nfull;
+    if (ng2 > kJointWords) ng2 = kJointWords;
+    if (ng2 < 4) ng2 = 0;
+    s.ng2 = ng2;
     if (rel < ng) {                            // member of a group: one segment ends the wave
       const int g = rel / nd.R, m = rel - g * nd.R;
       const int a = nd.a + g * nd.tpc;
       const int b = (a + nd.tpc < nd.t0) ? a + nd.tpc : nd.t0;
+      const bool top = it.node == 0;
       ++it.v; it.node = 0; it.pass = 0;
       if (rel >= 0 && a < b) {
         s.unit = u0 + m; s.vt0 = a; s.vt1 = b; s.j = nd.jbase + g;
+        s.jw = (top && 2 * g < ng2) ? 2 * g : -1;
         s.sync = c0 + g * nd.nwin_g; s.members = nd.R * p.cs;
         return true;
       }
@@ -105,6 +116,7 @@ MCL_HD bool seg_iter_next(const TcPlan& p, SegIter& it, Seg& s) {
     if (it.pass < nd.passes) {                 // tail worker: next pass over [t0, T)
       s.unit = u0 + it.pass * nd.wr + m; s.vt0 = nd.t0; s.vt1 = p.num_vt; s.j = nd.jbase + nd.nfull;
       s.sync = c0 + nd.nfull * nd.nwin_g + it.pass * nd.nwin_t; s.members = nd.wr * p.cs;
+      s.jw = -1;
       ++it.pass;
       return true;
     }

@@ -23,6 +23,7 @@
 // back to an exact radix select that keeps the earliest ties.
 #pragma once
 #include "common.cuh"
+#include "plan.h"
 
 namespace mcl {
 
@@ -146,8 +147,21 @@ __device__ __forceinline__ int warp_count_ge(const uint32_t (&key)[kCandCap / 32
 // the next chunk.  warp_buf = buffer of the warp's lane-0 row; rows are kCandCap apart.
 // tau_pub = this lane's word of the shared threshold array (nullable).  Must be called by
 // all 32 lanes (converged).
+//
+// Joint threshold (joint_warp != nullptr): a slot sees only 1/n of a row's columns, so its own
+// k-th best -- and the maximum of the slots' k-th bests, which tau_pub carries -- passes ~n times
+// more candidates than the row's true k-th best would.  Each of the first ng2 slot halves of a
+// wave therefore also publishes x_i, a key that at least m = ceil(k / ng2) of ITS entries reach
+// (the m-th largest of the 32 lane maxima of the buffer: m max-reductions, no extra loads).
+// Once all ng2 words of a row are set, min_i x_i is reached by >= ng2 * m >= k scores of the row
+// at distinct table rows, i.e. it is a lower bound of the row's k-th best -- about as tight as
+// the k-th best of ALL columns seen so far -- and every slot of the row filters with it
+// (scan_tc.cu).  joint_warp = the word of the warp's lane-0 row; rows are kJointWords apart.
+// Measured on B200 (profiles/README.md): ~3x fewer appends, but the per-tile reads and the stale
+// bound between compactions cost as much as they save except on C2; library option 12 turns it on.
 __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* warp_buf, int lane,
-                                                  uint32_t* tau_pub) {
+                                                  uint32_t* tau_pub, uint32_t* joint_warp = nullptr,
+                                                  int joint_m = 0) {
   unsigned need = __ballot_sync(0xffffffffu, st.cnt + kChunk > kCandCap);
   if (need == 0) return;
   const unsigned lt = (1u << lane) - 1u;
@@ -192,6 +206,16 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
     uint32_t mx = key[0];
 #pragma unroll
     for (int i = 1; i < kCandCap / 32; ++i) mx = max(mx, key[i]);
+    if (joint_warp) {                                // m-th largest lane maximum of the buffer
+      uint32_t v = mx, xj = 0u;
+      for (int t = 0; t < joint_m; ++t) {
+        xj = __reduce_max_sync(0xffffffffu, v);
+        const unsigned who = __ballot_sync(0xffffffffu, v == xj);
+        if (lane == __ffs(who) - 1) v = 0u;          // retire ONE lane holding it
+      }
+      // (lane maxima move when a buffer is repacked: keep the best bound ever established)
+      if (lane == 0 && xj > 1u) atomicMax(joint_warp + (size_t)r * kJointWords, xj);
+    }
     mx = __reduce_max_sync(0xffffffffu, mx);
     uint32_t lo = tau_key + 1u;                        // entries strictly above the threshold
     uint32_t hi = (mx == 0xffffffffu) ? mx : mx + 1u;  // #{key >= hi} = 0 < k

@@ -57,6 +57,7 @@ struct TcParams {
   unsigned long long* timing;   // nullable: [grid][2] globaltimer at CTA start / end
   uint32_t* tau_shared;         // [padded rows] order-preserving keys, zeroed before the launch
   int* sync_ctr;                // [plan_nctr] CTAs that started a window, zeroed
+  uint32_t* joint;              // [padded rows][kJointWords] joint-threshold words, zeroed (nullable)
   float softcap;                // 0 = off; c > 0: logits are c*tanh(z/c) (kCap instantiation)
   unsigned long long pol_q, pol_t;   // L2 eviction priority of the query / table tile loads
   float* small_scores;          // small-batch path (select.cu): [Q][small_ld] scores, top-k filter off
@@ -250,6 +251,15 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       // threshold word shared by all workers that scan this query row (other table tiles)
       uint32_t* tau_pub = p.tau_shared ? p.tau_shared + row : nullptr;
       uint32_t tau_seen = tau_pub ? __ldcg(tau_pub) : 0u;   // later segments start below a tight bound
+      // joint threshold of the row's slots (rowstate.cuh): read by every segment, published by
+      // the column halves of the wave's first groups
+      const int ng2 = p.joint ? sg.ng2 : 0;
+      const uint32_t* joint_row = ng2 ? p.joint + (size_t)row * kJointWords : nullptr;
+      uint32_t* joint_warp = (ng2 && sg.jw >= 0)
+          ? p.joint + ((size_t)rb * kBlockM + quarter * 32) * kJointWords + sg.jw + half : nullptr;
+      const int joint_m = ng2 ? (p.k + ng2 - 1) / ng2 : 0;
+      uint4 ja = make_uint4(0u, 0u, 0u, 0u), jb = ja;
+      if (joint_row) { ja = ld_cg_v4_pinned(joint_row); if (ng2 > 4) jb = ld_cg_v4_pinned(joint_row + 4); }
       const int next_vt0 = have_next ? nx.vt0 : -1;
       for (int vt = vt0; vt < vt1; ++vt) {
         // (both consume values requested one tile ago and request the next ones; the threshold
@@ -257,6 +267,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (tau_pub) {
           row_apply_shared_tau(st, tau_seen);
           tau_seen = ld_cg_u32_pinned(tau_pub);
+        }
+        if (joint_row) {
+          const uint32_t w[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+          uint32_t jmin = 0xffffffffu;
+          bool all_set = true;
+#pragma unroll
+          for (int i = 0; i < kJointWords; ++i)
+            if (i < ng2) { all_set = all_set && w[i] != 0u; jmin = min(jmin, w[i]); }
+          if (all_set) row_apply_shared_tau(st, jmin);
+          ja = ld_cg_v4_pinned(joint_row);
+          if (ng2 > 4) jb = ld_cg_v4_pinned(joint_row + 4);
         }
         if (p.inv_t) {
           if (cs_vt != vt) load_cs(vt);                // first tile of a run: exposed once
@@ -315,7 +336,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           else row_process_chunk<true, kCap>(st, y, col0, n_valid, a, lab_local, rc);
           __syncwarp();
           // (nothing follows the last chunk of the slot: leave its buffer to the merge)
-          if (!(vt + 1 == vt1 && c + 1 == nch)) warp_compact_rows(st, p.k, warp_buf, lane, tau_pub);
+          if (!(vt + 1 == vt1 && c + 1 == nch))
+            warp_compact_rows(st, p.k, warp_buf, lane, tau_pub, joint_warp, joint_m);
         };
 
         // TMEM -> registers one chunk at a time; the other epilogue warp on this scheduler
@@ -528,17 +550,19 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t e
   const size_t o_time = take(2 * 1024 * sizeof(unsigned long long));   // always at offset 0
   const size_t o_tau = take((size_t)num_rb * kBlockM * sizeof(uint32_t));
   const size_t o_ctr = take((size_t)nctr * sizeof(int));
+  const size_t o_joint = take((size_t)num_rb * kBlockM * kJointWords * sizeof(uint32_t));
   const size_t o_cand = take((size_t)nslots * kBlockM * kCandCap * sizeof(uint2));
   const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int2));
   const size_t o_stats = take((size_t)nslots * kBlockM * sizeof(float4));
   const size_t o_extra = take(extra_bytes);
   w.bytes = off;
-  w.zero_bytes = o_ctr + (((size_t)nctr * sizeof(int) + 255) & ~(size_t)255) - o_tau;
+  w.zero_bytes = o_joint + (((size_t)num_rb * kBlockM * kJointWords * sizeof(uint32_t) + 255) & ~(size_t)255) - o_tau;
   if (base) {
     uint8_t* b = (uint8_t*)base;
     w.timing = (void*)(b + o_time);
     w.tau_shared = (void*)(b + o_tau);
     w.sync_ctr = (void*)(b + o_ctr);
+    w.joint = (void*)(b + o_joint);
     w.sv.cand = (uint2*)(b + o_cand);
     w.sv.cnt = (int2*)(b + o_cnt);
     w.sv.stats = (float4*)(b + o_stats);
@@ -624,6 +648,7 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
   p.sv = sv; p.dbg_scores = a.dbg_scores; p.timing = (unsigned long long*)a.timing;
   p.tau_shared = (uint32_t*)a.tau_shared;
   p.sync_ctr = (int*)a.sync_ctr;
+  p.joint = (uint32_t*)a.joint;
   p.softcap = a.softcap;
   p.small_scores = a.small_scores; p.small_ld = (int)a.small_ld;
   p.pol_q = (a.l2_mode & 1) ? kL2EvictLast : kL2EvictNormal;

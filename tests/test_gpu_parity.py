@@ -193,9 +193,10 @@ def test_tc_zero_query_rows(mcl):
     assert abs(float(out.lse[0]) - math.log(4096)) < 1e-4
 
 
-@pytest.mark.parametrize("opt,value", [(1, 1), (1, 2), (1, 3), (0, 5), (0, 1), (0, 10), (7, 0)])
+@pytest.mark.parametrize("opt,value", [(1, 1), (1, 2), (1, 3), (0, 5), (0, 1), (0, 10), (7, 0), (12, 1)])
 def test_tc_schedules_are_equivalent(mcl, opt, value):
-    """Different tile plans (wave size / CTA count / tail workers) must give identical answers.
+    """Different tile plans (wave size / CTA count / tail workers) and the joint threshold on / off
+    must give identical answers.
     10 CTAs = 5 workers on 3 row units: one group, a tail pass and a second-level node."""
     q, t = make_inputs(700, 3000, 64, 27)
     old = mcl.set_option(opt, value)
