@@ -293,6 +293,52 @@ def test_full_size_properties_qwen2vl_scale(mcl):
     torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4)
 
 
+@pytest.mark.parametrize("name,Q,V,D,scale", [("c4", 65536, 128256, 4096, 1.0),
+                                              ("c5", 32768, 1048576, 1024, 100.0),
+                                              ("c5-ragged", 32768, 1000000, 1024, 100.0)])
+def test_full_size_multi_wave_plans(mcl, name, Q, V, D, scale):
+    """BASELINE configs[3] / [4] at full size: many waves, tail passes and second-level nodes of
+    the tile plan, which no oracle-sized shape reaches.  (1) planted exact matches spread over
+    every wave must be top-1 with cosine 1; (2) rows sampled from every part of the plan (first /
+    middle / last row blocks, i.e. groups, tail passes and deeper nodes) are checked against torch
+    fp32 on the GPU: top-k and log-sum-exp; (3) the plan without tail workers (a different
+    partition of every row's columns) must give the same values bit-for-bit."""
+    k = 50
+    g = torch.Generator(device="cuda").manual_seed(4000 + D)
+    q = torch.randn(Q, D, generator=g, device="cuda").to(torch.bfloat16)
+    t = torch.randn(V, D, generator=g, device="cuda").to(torch.bfloat16)
+    rows = torch.unique(torch.cat([torch.arange(0, 64), torch.arange(Q - 64, Q),
+                                   torch.linspace(0, Q - 1, 193).long()])).cuda()
+    plant = torch.randperm(V, generator=g, device="cuda")[:rows.numel()]
+    t[plant] = q[rows]
+    inv_t = mcl.row_inv_norm(t)
+    labels = torch.randint(0, V, (Q,), generator=g, device="cuda")
+    full = mcl.concept_scan(q, t, k, inv_norm_t=inv_t, scale=scale, labels=labels)
+    assert torch.equal(full.topk_idx[rows, 0], plant)
+    torch.testing.assert_close(full.topk_val[rows, 0], torch.full((rows.numel(),), scale, device="cuda"),
+                               rtol=RTOL, atol=0)
+    assert (full.topk_val[:, 1:] <= full.topk_val[:, :-1]).all()
+    assert int(full.topk_idx.min()) >= 0 and int(full.topk_idx.max()) < V
+    sub = rows[::5][:48]
+    tn = torch.nn.functional.normalize(t.float(), dim=1)
+    z = scale * (torch.nn.functional.normalize(q[sub].float(), dim=1) @ tn.T)
+    del tn
+    check_topk(full.topk_val[sub], full.topk_idx[sub], z, k, rtol=RTOL, atol=1e-5 * scale)
+    torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4 * scale)
+    torch.testing.assert_close(full.stats[sub, 3], z[torch.arange(sub.numel()), labels[sub]], rtol=RTOL,
+                               atol=1e-5 * scale)
+    del z
+    old = mcl.set_option(7, 0)
+    try:
+        other = mcl.concept_scan(q, t, k, inv_norm_t=inv_t, scale=scale, labels=labels)
+    finally:
+        mcl.set_option(7, old)
+    assert torch.equal(other.topk_val, full.topk_val)
+    differ = other.topk_idx != full.topk_idx                     # only among exact ties at the k-th value
+    assert not (differ & (full.topk_val != full.topk_val[:, -1:])).any()
+    torch.testing.assert_close(other.lse, full.lse, rtol=1e-6, atol=1e-5 * scale)
+
+
 # ---- soft-capped logits (SURVEY 8f-4) ----------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_softcap_logits(mcl, dtype):
