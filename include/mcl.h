@@ -91,7 +91,12 @@ int mcl_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t 
  *     topk_val[i,:], topk_idx[i,:]  the k largest z_ij, descending, exact ties broken by
  *                                   the lowest table row; idx = index_base + local row
  *     row_stats[i,:]                (m, s, sum_z, z_label) -- see MCL_STAT_*
- * The [Q x V] score matrix is never written to memory.  lse_i = m + log s;
+ * For batches of more than one row block (Q > 128) the [Q x V] score matrix is never written
+ * to memory: the top-k filter and the statistics run in the GEMM's epilogue.  Batches of one
+ * row block (the reference's 6..96 concept tokens) are bound by the table read, not by the
+ * scores: there the epilogue keeps the statistics and drops the Q x V_local scores -- a few
+ * percent of the table bytes, L2 resident -- into the workspace, and an exact selection kernel
+ * picks the top-k from them (same values, same tie rule; csrc/select.cu).  lse_i = m + log s;
  * CE_i = (1-eps)(lse_i - z_label) + eps (lse_i - sum_z / V) is formed by the caller.
  * Replaces, in one call:
  *   - sklearn `cosine_similarity` per pair   src/multimodal/token_embedding_analysis.py:237-246
