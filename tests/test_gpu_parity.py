@@ -425,3 +425,32 @@ def test_small_batch_selection_fallback_and_ties(mcl):
         order = sorted(range(V), key=lambda c: (-sc[c].item(), c))[:k]
         assert out.topk_idx[r].cpu().tolist() == order, f"row {r}"
         torch.testing.assert_close(out.topk_val[r].cpu().double(), sc[order], rtol=0, atol=0)
+
+
+# ---- edge cases of the domain -----------------------------------------------------------
+def test_empty_query_batch(mcl):
+    _, t = make_inputs(1, 500, 64, 80)
+    out = mcl.concept_scan(torch.empty(0, 64, dtype=torch.bfloat16, device="cuda"), t.cuda(), 10)
+    assert out.topk_val.shape == (0, 10) and out.topk_idx.shape == (0, 10) and out.stats.shape == (0, 4)
+
+
+@pytest.mark.parametrize("Q,V,D,k", [(3, 50, 64, 50), (200, 50, 64, 50), (130, 64, 128, 64), (2, 1, 8, 1)])
+def test_k_equals_table_rows(mcl, Q, V, D, k):
+    """k = V: every table row is returned, in (value desc, row asc) order -- through the
+    small-batch path (Q <= 128) and the streaming path."""
+    q, t = make_inputs(Q, V, D, 81 + Q)
+    out, ref = run_case(mcl, q, t, k)
+    assert (out.topk_idx.sort(dim=1).values.cpu() == torch.arange(V).expand(Q, V)).all()
+
+
+def test_all_labels_ignored_and_out_of_shard(mcl):
+    """ignore_index rows contribute nothing (loss is nan over an empty set, as F.cross_entropy);
+    labels that live in another shard leave z_label = 0 for the merge to fill in."""
+    q, t = make_inputs(140, 900, 64, 83)
+    labels = torch.full((140,), -100)
+    out, ref = run_case(mcl, q, t, 20, labels=labels)
+    assert torch.isnan(out.loss) and (out.stats[:, 3] == 0).all()
+    far = torch.randint(5000, 6000, (140,), generator=torch.Generator().manual_seed(83))
+    out2 = mcl.concept_scan(q.cuda(), t.cuda(), 20, labels=far, index_base=1000)
+    assert (out2.stats[:, 3] == 0).all()
+    assert torch.equal(out2.topk_idx, out.topk_idx + 1000)
