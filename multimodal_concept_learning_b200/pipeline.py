@@ -1,11 +1,12 @@
 """Streaming front end for host-resident query batches: overlaps the host->device copy of batch
 i+1 and the device->host copy of result i-1 with the scan of batch i (two CUDA streams, two
 device buffers, events -- no host synchronisation inside the loop except on the result that is
-handed back).  This is the path a caller with queries in pinned host memory uses; `bench.py`
+handed back, `lag` batches late).  This is the path a caller with queries in pinned host memory uses; `bench.py`
 measures its `e2e` number through it.  With a sharded scanner every rank uploads 1/N of the batch and
 the ranks all-gather it over NVLink."""
 from __future__ import annotations
 
+import collections
 from typing import Iterable, Iterator, Optional, Tuple
 
 import torch
@@ -15,12 +16,15 @@ from . import ops
 
 class HostQueryPipeline:
     def __init__(self, table: torch.Tensor, k: int, *, normalize: bool = True, scale: float = 1.0,
-                 inv_norm_t: Optional[torch.Tensor] = None, scanner=None):
+                 inv_norm_t: Optional[torch.Tensor] = None, scanner=None, lag: int = 3):
         if not table.is_cuda:
             raise RuntimeError("table must be a CUDA tensor (no CPU fallback)")
         self.table, self.k, self.normalize, self.scale = table, int(k), normalize, float(scale)
         self.device = table.device
         self.scanner = scanner            # an optional sharded.ShardedConceptScan
+        # results handed back `lag` batches late: the host thread may run that far ahead of the
+        # device, which hides its jitter (8 ranks + NCCL proxy threads share the host cores)
+        self.lag = max(1, int(lag))
         self.inv_norm_t = inv_norm_t
         if normalize and inv_norm_t is None and scanner is None:
             self.inv_norm_t = ops.row_inv_norm(table)
@@ -39,7 +43,7 @@ class HostQueryPipeline:
         """Yields (topk_val, topk_idx, stats) as pinned HOST tensors, one per input batch, in
         order.  Each host batch should be pinned for the copies to be asynchronous."""
         main = torch.cuda.current_stream(self.device)
-        pending = None                    # (host results, event) of the previous batch
+        pending = collections.deque()     # (host results, event) of the batches in flight
         it = iter(host_batches)
         nxt = next(it, None)
         slot = 0
@@ -65,13 +69,15 @@ class HostQueryPipeline:
                 copied.record(self.copy_stream)
             for t in (out.topk_val, out.topk_idx, out.stats):
                 t.record_stream(self.copy_stream)
-            if pending is not None:
-                pending[1].synchronize()
-                yield pending[0]
-            pending = (host, copied)
-        if pending is not None:
-            pending[1].synchronize()
-            yield pending[0]
+            pending.append((host, copied))
+            while len(pending) > self.lag:
+                res, ev = pending.popleft()
+                ev.synchronize()
+                yield res
+        while pending:
+            res, ev = pending.popleft()
+            ev.synchronize()
+            yield res
 
     def _stage(self, host_q: torch.Tensor, slot: int, main):
         buf = self._bufs[slot]

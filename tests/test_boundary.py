@@ -154,3 +154,55 @@ def test_small_cta_counts_plan_tail_workers(lib_built):
     with_tail = [p for p in plans if p["last"][0]["wr"] > 0]
     assert len(with_tail) >= 2, [p["last"] for p in plans]
     assert any(len(p["last"]) >= 2 for p in with_tail), "no plan with a second-level node"
+
+
+def _check_plan(lib, _lib, Q, V, D, sm):
+    """Every (row block, tile) exactly once; one writer per slot; merge-side slot map exact."""
+    p = _lib.plan_scan(Q, V, D, sm)
+    segs = _lib.plan_segments(Q, V, D, sm)
+    cs, S, T = p["cs"], p["S"], p["num_vt"]
+    assert 1 <= p["grid"] <= sm and p["workers"] * cs == p["grid"]
+    covered = {}
+    slots = {}
+    workers = set()
+    for w, unit, vt0, vt1, j, sync in segs:
+        assert 0 <= w < p["workers"] and 0 <= unit < p["ru"] and 0 <= vt0 < vt1 <= T and 0 <= j < S
+        assert 0 <= sync < max(1, p["nctr"])
+        workers.add(w)
+        assert (unit, j) not in slots, "two segments end in one slot"
+        slots[(unit, j)] = (vt0, vt1)
+        covered.setdefault(unit, []).append((vt0, vt1))
+    assert len(workers) == p["workers"]
+    for unit in range(p["ru"]):
+        iv = sorted(covered.get(unit, []))
+        assert iv and iv[0][0] == 0 and iv[-1][1] == T, (unit, iv)
+        assert all(a[1] == b[0] for a, b in zip(iv, iv[1:])), f"row unit {unit}: gap or overlap {iv}"
+        js = sorted(j for (u, j) in slots if u == unit)
+        assert js == list(range(len(js))), f"row unit {unit}: slots {js} not dense"
+        for crank in range(cs):
+            rb = unit * cs + crank
+            if rb >= p["num_rb"]:
+                continue
+            a, b = C.c_int32(), C.c_int32()
+            assert lib.mcl_plan_row_block_slots(Q, V, D, sm, rb, C.byref(a), C.byref(b)) == 0
+            assert a.value == rb * S * 2 and b.value == 2 * len(js)
+
+
+def test_plan_fuzz(lib_built):
+    """The closed-form tile plan on random shapes and SM counts (hypothesis): the properties the
+    scan kernel and the merge rely on hold for every plan the host can produce."""
+    from hypothesis import given, settings, strategies as st
+    from multimodal_concept_learning_b200 import _lib
+    lib = _lib.load()
+
+    @settings(max_examples=120, deadline=None)
+    @given(Q=st.one_of(st.integers(1, 600), st.integers(1, 40000)),
+           V=st.one_of(st.integers(1, 3000), st.integers(1, 400000)),
+           D=st.sampled_from([8, 64, 72, 768, 1152, 3584, 4096]),
+           sm=st.one_of(st.integers(1, 12), st.sampled_from([132, 148, 160])))
+    def run(Q, V, D, sm):
+        if (-(-Q // 128)) * (-(-V // 256)) > 60000:       # keep the enumeration small
+            V = max(1, 60000 * 256 // (-(-Q // 128)))
+        _check_plan(lib, _lib, Q, V, D, sm)
+
+    run()
