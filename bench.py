@@ -194,7 +194,9 @@ def run_workload(name, steps, warmup, world, rank, device, with_e2e=True, sample
         pipe = HostQueryPipeline(table, K_TOP, normalize=w["normalize"], scale=w["scale"],
                                  inv_norm_t=step.inv_t, scanner=step.scanner)
         outs = None
-        for outs in pipe.run((q_host for _ in range(max(2, warmup // 2))), labels):
+        # (warm-up long enough for the pinned result buffers of all batches in flight to come from
+        # torch's host-allocator cache: a cudaHostAlloc inside the timed region costs milliseconds)
+        for outs in pipe.run((q_host for _ in range(max(8, warmup))), labels):
             pass
         torch.cuda.synchronize(device)
         if world > 1:
