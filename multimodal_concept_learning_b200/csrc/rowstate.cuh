@@ -28,6 +28,9 @@
 namespace mcl {
 
 constexpr int kSlack = 14;   // a compaction leaves k .. k+kSlack entries
+#ifndef MCL_APPEND_GROUP
+#define MCL_APPEND_GROUP 8   // columns per append group (4 and 8 measured: profiles/README.md)
+#endif
 
 // 2^x on the SFU (MUFU.EX2), one instruction: ~2 ulp, flushes results below 2^-126 to 0,
 // which is far inside the rtol of a sum of >= 1 terms of magnitude 1 (the row max).
@@ -64,15 +67,23 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
     for (int i = 0; i < kChunk; ++i)
       if (i >= n_valid) y[i] = -INFINITY;
   }
-  // maxima of the four groups of 8 columns (they also steer the candidate append below)
-  float gm[kChunk / 8];
+  // maxima of the groups of kGroup columns (they also steer the candidate append below)
+  constexpr int kGroup = MCL_APPEND_GROUP, kGroups = kChunk / kGroup;
+  float gm[kGroups];
 #pragma unroll
-  for (int g = 0; g < kChunk / 8; ++g) {
-    const float m01 = fmaxf(y[8 * g], y[8 * g + 1]), m23 = fmaxf(y[8 * g + 2], y[8 * g + 3]);
-    const float m45 = fmaxf(y[8 * g + 4], y[8 * g + 5]), m67 = fmaxf(y[8 * g + 6], y[8 * g + 7]);
-    gm[g] = fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+  for (int g = 0; g < kGroups; ++g) {
+    float m4[kGroup / 4];
+#pragma unroll
+    for (int h = 0; h < kGroup / 4; ++h)
+      m4[h] = fmaxf(fmaxf(y[kGroup * g + 4 * h], y[kGroup * g + 4 * h + 1]),
+                    fmaxf(y[kGroup * g + 4 * h + 2], y[kGroup * g + 4 * h + 3]));
+    gm[g] = m4[0];
+#pragma unroll
+    for (int h = 1; h < kGroup / 4; ++h) gm[g] = fmaxf(gm[g], m4[h]);
   }
-  const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+  float cm = gm[0];
+#pragma unroll
+  for (int g = 1; g < kGroups; ++g) cm = fmaxf(cm, gm[g]);
 
   // label column (at most once per row and slot)
   if (lab_local >= col0 && lab_local < col0 + kChunk) {
@@ -112,20 +123,20 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
   st.sum_y += (sy[0] + sy[1]) + (sy[2] + sy[3]);
 
   // lazy-threshold candidate append.  In steady state a warp's 32 rows hold one or two
-  // candidates per chunk between them: only the groups of 8 columns that contain one run
+  // candidates per chunk between them: only the groups of kGroup columns that contain one run
   // the store sequence (column order is kept: the tie rule relies on it).
-  // The group decisions are made warp-wide (one REDUX of a 4-bit mask): uniform branches need
+  // The group decisions are made warp-wide (one REDUX of the group mask): uniform branches need
   // no reconvergence barriers, which cost more than the predicated-off stores they would skip.
   unsigned gmask = 0u;
 #pragma unroll
-  for (int g = 0; g < kChunk / 8; ++g) gmask |= (gm[g] > st.tau) ? (1u << g) : 0u;
+  for (int g = 0; g < kGroups; ++g) gmask |= (gm[g] > st.tau) ? (1u << g) : 0u;
   gmask = __reduce_or_sync(0xffffffffu, gmask);
   if (gmask) {
 #pragma unroll
-    for (int g = 0; g < kChunk / 8; ++g) {
+    for (int g = 0; g < kGroups; ++g) {
       if (gmask & (1u << g)) {
 #pragma unroll
-        for (int i = 8 * g; i < 8 * g + 8; ++i) {
+        for (int i = kGroup * g; i < kGroup * g + kGroup; ++i) {
           if (y[i] > st.tau) {
             st.buf[st.cnt] = make_uint2(__float_as_uint(y[i]), (uint32_t)(col0 + i));
             ++st.cnt;
