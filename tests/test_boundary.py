@@ -206,3 +206,37 @@ def test_plan_fuzz(lib_built):
         _check_plan(lib, _lib, Q, V, D, sm)
 
     run()
+
+
+def test_header_is_plain_c_and_links(lib_built, tmp_path):
+    """include/mcl.h is the boundary a non-Python host binds: it must compile as C99, and a C
+    program linked against the .so must be able to call the host-only entry points."""
+    import shutil
+    import subprocess
+    from multimodal_concept_learning_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "mcl.h"
+int main(void) {
+  int32_t plan[MCL_PLAN_INTS];
+  if (mcl_version() != MCL_VERSION) return 1;
+  if (mcl_plan_scan(8192, 152064, 3584, 148, plan) != MCL_OK) return 2;
+  if (plan[0] != 64 || plan[1] != 594 || plan[2] != 56) return 3;           /* row blocks, tiles, K slices */
+  if (mcl_plan_scan(0, 1, 1, 148, plan) != MCL_ERR_BAD_ARG) return 4;
+  if (mcl_last_error()[0] == 0) return 5;
+  if (mcl_sharded_gather_bytes(8192, 50, 8) == 0) return 6;
+  printf("grid %d workers %d\\n", plan[10], plan[4]);
+  return 0;
+}
+''')
+    exe = tmp_path / "t"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe),
+                    f"-L{libdir}", "-l:libmcl_sm100.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "grid 148" in out.stdout
