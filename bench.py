@@ -206,7 +206,7 @@ def run_workload(name, steps, warmup, world, rank, device, with_e2e=True, sample
         from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
         q_host = q.cpu().pin_memory()
         pipe = HostQueryPipeline(table, K_TOP, normalize=w["normalize"], scale=w["scale"],
-                                 inv_norm_t=step.inv_t, scanner=step.scanner)
+                                 inv_norm_t=step.inv_t, scanner=step.scanner, reuse_host_buffers=True)
         outs = None
         # (warm-up long enough for the pinned result buffers of all batches in flight to come from
         # torch's host-allocator cache: a cudaHostAlloc inside the timed region costs milliseconds)

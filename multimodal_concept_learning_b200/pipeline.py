@@ -16,7 +16,8 @@ from . import ops
 
 class HostQueryPipeline:
     def __init__(self, table: torch.Tensor, k: int, *, normalize: bool = True, scale: float = 1.0,
-                 inv_norm_t: Optional[torch.Tensor] = None, scanner=None, lag: int = 3):
+                 inv_norm_t: Optional[torch.Tensor] = None, scanner=None, lag: int = 3,
+                 reuse_host_buffers: bool = False):
         if not table.is_cuda:
             raise RuntimeError("table must be a CUDA tensor (no CPU fallback)")
         self.table, self.k, self.normalize, self.scale = table, int(k), normalize, float(scale)
@@ -25,6 +26,12 @@ class HostQueryPipeline:
         # results handed back `lag` batches late: the host thread may run that far ahead of the
         # device, which hides its jitter (8 ranks + NCCL proxy threads share the host cores)
         self.lag = max(1, int(lag))
+        # False: every result is a fresh pinned tensor the caller owns.  True: results rotate through
+        # lag + 2 pinned buffer sets allocated once -- a yielded result is then valid until lag + 1
+        # more have been yielded (no pinned allocation in the loop: cudaHostAlloc maps the block into
+        # every visible GPU and costs milliseconds on an 8-GPU box)
+        self.reuse_host_buffers = bool(reuse_host_buffers)
+        self._host_ring, self._host_next = [], 0
         self.inv_norm_t = inv_norm_t
         if normalize and inv_norm_t is None and scanner is None:
             self.inv_norm_t = ops.row_inv_norm(table)
@@ -63,8 +70,8 @@ class HostQueryPipeline:
             done.record(main)
             self.copy_stream.wait_event(done)
             with torch.cuda.stream(self.copy_stream):                            # D2H of i
-                host = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                             .copy_(t, non_blocking=True) for t in (out.topk_val, out.topk_idx, out.stats))
+                host = tuple(h.copy_(t, non_blocking=True) for h, t in
+                             zip(self._host_set(out), (out.topk_val, out.topk_idx, out.stats)))
                 copied = torch.cuda.Event()
                 copied.record(self.copy_stream)
             for t in (out.topk_val, out.topk_idx, out.stats):
@@ -78,6 +85,18 @@ class HostQueryPipeline:
             res, ev = pending.popleft()
             ev.synchronize()
             yield res
+
+    def _host_set(self, out):
+        shapes = [(t.shape, t.dtype) for t in (out.topk_val, out.topk_idx, out.stats)]
+        if not self.reuse_host_buffers:
+            return [torch.empty(sh, dtype=dt, pin_memory=True) for sh, dt in shapes]
+        if not self._host_ring or [(h.shape, h.dtype) for h in self._host_ring[0]] != shapes:
+            self._host_ring = [[torch.empty(sh, dtype=dt, pin_memory=True) for sh, dt in shapes]
+                               for _ in range(self.lag + 2)]
+            self._host_next = 0
+        hs = self._host_ring[self._host_next]
+        self._host_next = (self._host_next + 1) % len(self._host_ring)
+        return hs
 
     def _stage(self, host_q: torch.Tensor, slot: int, main):
         buf = self._bufs[slot]

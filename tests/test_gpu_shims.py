@@ -190,16 +190,20 @@ def test_f1_lm_head_shim_trains_the_table():
     assert not ev.loss.requires_grad
 
 
-def test_host_query_pipeline_matches_direct_scan():
+@pytest.mark.parametrize("reuse", [False, True])
+def test_host_query_pipeline_matches_direct_scan(reuse):
+    """Fresh pinned results per batch, or a ring of lag + 2 reused result sets (each result is
+    then checked as it is yielded, before the ring wraps)."""
     import multimodal_concept_learning_b200 as mcl
     from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
     g = torch.Generator().manual_seed(70)
     table = torch.randn(5000, 128, generator=g).to(torch.bfloat16).cuda()
-    batches = [torch.randn(200, 128, generator=g).to(torch.bfloat16).pin_memory() for _ in range(5)]
-    pipe = HostQueryPipeline(table, 20, scale=10.0)
-    got = list(pipe.run(batches))
-    assert len(got) == 5
-    for b, (val, idx, stats) in zip(batches, got):
-        ref = mcl.concept_scan(b.cuda(), table, 20, scale=10.0)
+    batches = [torch.randn(200, 128, generator=g).to(torch.bfloat16).pin_memory() for _ in range(9)]
+    refs = [mcl.concept_scan(b.cuda(), table, 20, scale=10.0) for b in batches]
+    pipe = HostQueryPipeline(table, 20, scale=10.0, lag=2, reuse_host_buffers=reuse)
+    n = 0
+    for ref, (val, idx, stats) in zip(refs, pipe.run(batches)):
         assert not val.is_cuda and torch.equal(val, ref.topk_val.cpu()) and torch.equal(idx, ref.topk_idx.cpu())
         torch.testing.assert_close(stats, ref.stats.cpu(), rtol=1e-6, atol=1e-6)
+        n += 1
+    assert n == 9
