@@ -11,7 +11,8 @@
  *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless marked
  *     "host"; sizes are in elements; matrices are row-major with the inner dim contiguous.
  *   - the caller owns every buffer (inputs, outputs, workspace); the library never
- *     allocates or frees device memory and never synchronises the stream.
+ *     allocates or frees device memory (one explicit exception: mcl_peer_alloc / mcl_peer_free,
+ *     below) and never synchronises the stream.
  *   - every call returns 0 on success or a negative MCL_ERR_* code; a message is kept in a
  *     thread-local string readable with mcl_last_error().  No C++ exception crosses the ABI.
  *   - there is no CPU fallback: on a device that is not compute capability 10.x the compute
@@ -157,10 +158,24 @@ int mcl_similarity_matrix(const void* q, const void* table, int dtype, int64_t Q
 /*
  * Merge R partial results (one per vocabulary shard): candidates are re-ranked by
  * (value desc, index asc); m* = max m_r, s* = sum s_r exp(m_r - m*); sum_z and z_label add.
- * val/idx/stats are [R,Q,k] / [R,Q,k] / [R,Q,4]; idx < 0 marks an empty candidate.
+ * val/idx/stats are [R,Q,k] / [R,Q,k] / [R,Q,4]; idx < 0 marks an empty candidate; indices must be
+ * below 2^32 (they are packed into the low word of the 64-bit sort keys).
  */
 int mcl_merge(const float* val, const int64_t* idx, const float* stats, int R, int64_t Q, int k,
               float* out_val, int64_t* out_idx, float* out_stats, mcl_stream_t stream);
+
+/*
+ * Cross-entropy from row_stats (one launch, deterministic): loss_rows[i] =
+ * (1-eps)(lse_i - z_label_i) + eps (lse_i - sum_z_i / vocab), 0 where labels[i] == -100 (nullable
+ * output); loss_mean[0] = mean over the rows with a label (NaN if there is none, as torch),
+ * loss_mean[1] = their number.
+ * Replaces: `F.cross_entropy(logits.float(), shifted_labels, ignore_index=-100)` inside
+ *   ForCausalLMLoss reached from src/multimodal/mllm.py:115-120, and
+ *   `nn.CrossEntropyLoss(label_smoothing=eps)` at src/vision/vision_training.py:81-83,116.
+ */
+int mcl_ce_from_stats(const float* row_stats /*[Q,4]*/, const int64_t* labels /*[Q]*/, int64_t Q,
+                      float label_smoothing, int64_t vocab, float* loss_rows /*[Q] nullable*/,
+                      float* loss_mean /*[2]*/, mcl_stream_t stream);
 
 /*
  * Vocabulary-sharded scan over the GPUs of one NVSwitch box: local scan, ONE ncclAllGather
@@ -194,6 +209,49 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
                              mcl_stream_t stream);
 
 /*
+ * Same, with flags.  MCL_SHARDED_LOCAL_ROWS: with the row exchange (world > 2, Q % world == 0)
+ * rank r merges query rows [r*Q/world, (r+1)*Q/world) only; the flag skips the final all-gather of
+ * the merged rows, so only that row range of topk_val / topk_idx / row_stats is written -- for
+ * consumers that take each rank's rows separately (host copies of 1/world of the result per rank).
+ * Without the row exchange every rank merges every row and the flag changes nothing.
+ */
+#define MCL_SHARDED_LOCAL_ROWS 1
+int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtype, int64_t Q,
+                                int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                                const float* inv_norm_q, const float* inv_norm_t, float scale,
+                                int k, int64_t index_base, const int64_t* labels,
+                                float* topk_val, int64_t* topk_idx, float* row_stats,
+                                void* workspace, size_t workspace_bytes, void* gather_buf,
+                                size_t gather_bytes, void* comm, int world, int rank, int flags,
+                                mcl_stream_t stream);
+
+/*
+ * Peer exchange of replicated query batches without SMs.  A sharded scan needs the whole query
+ * batch on every GPU; when the batch arrives from the host, every rank uploads 1/N of it over
+ * its own PCIe link and PUSHES that slice into the staging buffer of every peer with copy-engine
+ * copies over NVLink (cudaMemcpyAsync on a side stream, overlapping the previous scan), followed
+ * by a 4-byte step counter into the peer's flag word; the consumer's stream waits on its own flag
+ * words with a stream memory operation.  No kernel, no NCCL call, no SM is involved.
+ *   mcl_peer_alloc   cudaMalloc + zero + cudaIpcGetMemHandle: the ONE kind of device memory the
+ *                    library allocates, because IPC handles need a plain cudaMalloc block (a
+ *                    framework's caching / virtual-memory allocator does not give one);
+ *                    freed by mcl_peer_free.  ipc_handle_out: MCL_IPC_HANDLE_BYTES host bytes,
+ *                    distributed by the caller (torch.distributed in the Python host layer).
+ *   mcl_peer_open    maps another rank's block into this process (cudaIpcOpenMemHandle).
+ *   mcl_memcpy_async cudaMemcpyAsync(cudaMemcpyDefault) on `stream`: local, peer or pinned-host
+ *                    pointers (UVA).
+ *   mcl_stream_wait_value32   `stream` waits until (int32)(*dev_addr - value) >= 0
+ *                    (cuStreamWaitValue32, GEQ): no host involvement, no spinning kernel.
+ */
+#define MCL_IPC_HANDLE_BYTES 64
+int mcl_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out /*host, 64 B*/);
+int mcl_peer_free(void* dev_ptr);
+int mcl_peer_open(const void* ipc_handle /*host, 64 B*/, void** peer_ptr);
+int mcl_peer_close(void* peer_ptr);
+int mcl_memcpy_async(void* dst, const void* src, size_t bytes, mcl_stream_t stream);
+int mcl_stream_wait_value32(mcl_stream_t stream, const void* dev_addr, uint32_t value);
+
+/*
  * Tuning knobs (host-side, process-global).  opt: 0 = CTAs per launch (0 = all SMs),
  * 1 = row units per wave of the tile plan (0 = heuristic), 2 = route bf16 inputs
  * through the CUDA-core check kernel instead of tcgen05 (tests only), 3 = record per-CTA
@@ -205,9 +263,12 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
  * tiles evict-last, bit 1: table tiles evict-first), 10 = drift window in tiles (0 = heuristic),
  * 11 = 1 sends one-row-block batches through the streaming top-k path instead of the score-dump +
  * radix-select path (tests, A/B), 12 = 1 turns the joint threshold of a row's slots on (rowstate.cuh; measured: +3 % on C2,
- * -3..-6 % elsewhere, so off by default);
+ * -3..-6 % elsewhere, so off by default), 13 = 1 turns the threshold-seeding pre-pass off, 14 = 1 sends
+ * k = 1 scans through the general top-k epilogue instead of the running-argmax one (tests, A/B);
  * opt 100..102 read the last memset / scan / merge
- * time in ns.  Returns the old value.
+ * time in ns; opt 103 reads how many drift waits of the scan kernel timed out (group members
+ * that lost L2 locality because a peer CTA was not resident) since the process started.
+ * Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);
 

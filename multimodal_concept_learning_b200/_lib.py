@@ -48,6 +48,7 @@ SIGNATURES = {
     "mcl_similarity_matrix": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32,
                                      _ptr, _ptr, _sz, _ptr]),
     "mcl_merge": (_i32, [_ptr, _ptr, _ptr, _i32, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "mcl_ce_from_stats": (_i32, [_ptr, _ptr, _i64, _f32, _i64, _ptr, _ptr, _ptr]),
     "mcl_comm_unique_id": (_i32, [_ptr]),
     "mcl_comm_init": (_i32, [_ptr, _i32, _i32, C.POINTER(_ptr)]),
     "mcl_comm_destroy": (_i32, [_ptr]),
@@ -56,6 +57,15 @@ SIGNATURES = {
     "mcl_concept_scan_sharded": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
                                         _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr,
                                         _sz, _ptr, _i32, _i32, _ptr]),
+    "mcl_concept_scan_sharded_ex": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
+                                           _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr,
+                                           _sz, _ptr, _i32, _i32, _i32, _ptr]),
+    "mcl_peer_alloc": (_i32, [_sz, C.POINTER(_ptr), _ptr]),
+    "mcl_peer_free": (_i32, [_ptr]),
+    "mcl_peer_open": (_i32, [_ptr, C.POINTER(_ptr)]),
+    "mcl_peer_close": (_i32, [_ptr]),
+    "mcl_memcpy_async": (_i32, [_ptr, _ptr, _sz, _ptr]),
+    "mcl_stream_wait_value32": (_i32, [_ptr, _ptr, C.c_uint32]),
     "mcl_set_option": (_i64, [_i32, _i64]),
     "mcl_launch_count": (_i64, []),
     "mcl_plan_scan": (_i32, [_i64, _i64, _i64, _i32, C.POINTER(C.c_int32)]),

@@ -18,6 +18,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
 std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0}, g_opt_joint{0};
+std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
@@ -89,9 +90,13 @@ struct ScanLayout {
   bool tc; TcPlan plan; int nsplit, nslots, rows_padded, nctr;
   // small-batch path (select.cu): one row block, scores dumped [Q][small_ld] + per-range lists
   bool small; int64_t small_ld; int splits; size_t scores_bytes, extra_bytes;
+  int mode;            // epilogue mode of the tcgen05 scan: top-k / top-1 (k == 1)
+  // threshold seeding pre-pass (scan_tc_kernel.cuh, kModeSeed): seed_tiles sample tiles, every
+  // seed_stride-th tile of the table, scanned with a plan of their own
+  bool seed; TcPlan seed_plan; int seed_tiles, seed_stride; int64_t seed_ld; size_t seed_bytes;
 };
 constexpr size_t kSmallScoreBytesMax = 64u << 20;   // the dump must stay L2 resident
-ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int dtype, int sm) {
+ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int k, int dtype, int sm) {
   ScanLayout L{};
   L.tc = use_tc(dtype);
   const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
@@ -100,9 +105,24 @@ ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int dtype, int sm) {
     L.nslots = plan_nslots(L.plan);
     L.rows_padded = L.plan.ru * L.plan.cs;
     L.nctr = plan_nctr(L.plan);
+    L.mode = (k == 1 && !g_opt_notop1.load()) ? 1 : 0;
     L.small_ld = (V + kChunk - 1) / kChunk * kChunk;
     L.scores_bytes = (((size_t)Q * L.small_ld * sizeof(float)) + 255) & ~(size_t)255;
-    L.small = num_rb == 1 && L.scores_bytes <= kSmallScoreBytesMax && !g_opt_nosmall.load();
+    // (k = 1 needs no score dump: the running argmax of the top-1 epilogue is the answer)
+    L.small = num_rb == 1 && L.mode == 0 && L.scores_bytes <= kSmallScoreBytesMax && !g_opt_nosmall.load();
+    // Seeding pays where the epilogue, not the tensor pipe, bounds the scan (D <= 1536) and the
+    // sample -- ~2.5 k chunk maxima per row, at most 16 tiles -- is under a tenth of the table.
+    const int nt = std::min(16, (5 * k / 2 + 7) / 8);
+    if (!L.small && L.mode == 0 && !g_opt_noseed.load() && L.plan.num_kb <= 24 && nt >= 1 &&
+        nt * 8 >= k && L.plan.num_vt >= 10 * nt) {
+      L.seed = true;
+      L.seed_tiles = nt;
+      L.seed_stride = (L.plan.num_vt - 1) / nt;          // never the last (ragged) tile
+      L.seed_plan = make_tc_plan(Q, (int64_t)nt * kBlockN, D, sm, knobs());
+      L.seed_ld = (int64_t)std::max(L.rows_padded, L.seed_plan.ru * L.seed_plan.cs) * kBlockM;
+      L.seed_bytes = (((size_t)nt * (kBlockN / kChunk) * L.seed_ld * sizeof(uint32_t)) + 255) & ~(size_t)255;
+      L.extra_bytes = L.seed_bytes;
+    }
     if (L.small) {
       L.splits = select_splits(V);
       // lists sized for k = MCL_MAX_K: the workspace query does not depend on k
@@ -150,7 +170,7 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   DevInfo di;
   if ((rc = require_sm100(&di))) return rc;
   if (Q == 0) return MCL_OK;
-  const ScanLayout L = scan_layout(Q, V, D, dtype, di.sm);
+  const ScanLayout L = scan_layout(Q, V, D, k, dtype, di.sm);
   Workspace ws = carve_workspace(workspace, L.nslots, L.rows_padded, L.nctr, L.extra_bytes);
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
@@ -158,7 +178,7 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
              g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr,
              g_opt_joint.load() ? ws.joint : nullptr, softcap,
-             (int)g_opt_l2.load(), nullptr, 0};
+             (int)g_opt_l2.load(), nullptr, 0, L.mode, 1, nullptr, 0};
   // Small batches (one row block) without a caller-side score dump: the scan keeps only the
   // statistics and drops the scores into the workspace; select.cu picks the top-k from them.
   const bool small = L.small && !dbg;
@@ -173,9 +193,26 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   }
   if (L.tc) {
     char msg[256] = "";
-    e = launch_zero(ws.tau_shared, ws.zero_bytes, stream);
-    if (e != cudaSuccess) return cuda_fail(e, "clearing the shared thresholds");
-    g_launches++;
+    if (L.seed && !dbg) {
+      // threshold seeding: sample scan -> chunk maxima -> k-th largest per row into the shared
+      // threshold words (the same kernel clears the drift counters and joint words)
+      ScanArgs sa = a;
+      sa.mode = 2; sa.tile_stride = L.seed_stride; sa.seed_max = ws.extra; sa.seed_ld = L.seed_ld;
+      sa.labels = nullptr; sa.timing = nullptr; sa.dbg_scores = nullptr; sa.small_scores = nullptr;
+      e = launch_scan_tc(sa, L.seed_plan, ws.sv, stream, msg, sizeof(msg));
+      if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "seed scan launch: %s %s", cudaGetErrorString(e), msg);
+      g_launches++;
+      e = launch_seed_select((const uint32_t*)ws.extra, L.seed_tiles * (kBlockN / kChunk), L.seed_ld,
+                             (int64_t)L.rows_padded * kBlockM, k, (uint32_t*)ws.tau_shared, ws.sync_ctr,
+                             ws.zero_bytes - ((char*)ws.sync_ctr - (char*)ws.tau_shared), stream);
+      if (e != cudaSuccess) return cuda_fail(e, "seed select launch");
+      g_launches++;
+    } else if (L.mode == 0 || L.plan.ru > 1) {
+      // (a k = 1 scan of a single row unit reads neither thresholds nor drift counters)
+      e = launch_zero(ws.tau_shared, ws.zero_bytes, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "clearing the shared thresholds");
+      g_launches++;
+    }
     if (phases) cudaEventRecord(ev[1], stream);
     e = launch_scan_tc(a, L.plan, ws.sv, stream, msg, sizeof(msg));
     if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "scan_tc launch: %s %s", cudaGetErrorString(e), msg);
@@ -321,11 +358,10 @@ int mcl_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t 
 }
 
 size_t mcl_scan_workspace_bytes(int64_t Q, int64_t V_local, int64_t D, int k, int dtype) {
-  (void)k;
   DevInfo di;
   if (!dev_info(&di)) { cudaGetLastError(); di.sm = 148; }
   if (Q <= 0 || V_local <= 0 || D <= 0) return 256;
-  const ScanLayout L = scan_layout(Q, V_local, D, dtype, di.sm);
+  const ScanLayout L = scan_layout(Q, V_local, D, k < 1 ? 1 : k, dtype, di.sm);
   return carve_workspace(nullptr, L.nslots, L.rows_padded, L.nctr, L.extra_bytes).bytes;
 }
 
@@ -397,6 +433,22 @@ int mcl_merge(const float* val, const int64_t* idx, const float* stats, int R, i
   return MCL_OK;
 }
 
+int mcl_ce_from_stats(const float* row_stats, const int64_t* labels, int64_t Q, float label_smoothing,
+                      int64_t vocab, float* loss_rows, float* loss_mean, mcl_stream_t stream) {
+  if (Q < 0 || vocab < 1 || !(label_smoothing >= 0.f) || !(label_smoothing <= 1.f))
+    return fail(MCL_ERR_BAD_ARG, "bad Q / vocab / label_smoothing");
+  if (!loss_mean || (Q > 0 && (!row_stats || !labels))) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  if (!aligned16(row_stats)) return fail(MCL_ERR_UNALIGNED, "row_stats must be 16-byte aligned");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  cudaError_t e = launch_ce_from_stats(row_stats, labels, Q, label_smoothing, vocab, loss_rows, loss_mean,
+                                       (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "ce_from_stats launch");
+  g_launches++;
+  return MCL_OK;
+}
+
 int mcl_comm_unique_id(void* unique_id_out) {
   NcclApi* n = nccl();
   if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror() ? dlerror() : "");
@@ -453,7 +505,23 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
                              int64_t* topk_idx, float* row_stats, void* workspace,
                              size_t workspace_bytes, void* gather_buf, size_t gather_bytes,
                              void* comm, int world, int rank, mcl_stream_t stream) {
+  return mcl_concept_scan_sharded_ex(q, table_shard, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t,
+                                     scale, k, index_base, labels, topk_val, topk_idx, row_stats, workspace,
+                                     workspace_bytes, gather_buf, gather_bytes, comm, world, rank, 0, stream);
+}
+
+int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtype, int64_t Q,
+                                int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                                const float* inv_norm_q, const float* inv_norm_t, float scale, int k,
+                                int64_t index_base, const int64_t* labels, float* topk_val,
+                                int64_t* topk_idx, float* row_stats, void* workspace,
+                                size_t workspace_bytes, void* gather_buf, size_t gather_bytes,
+                                void* comm, int world, int rank, int flags, mcl_stream_t stream) {
   if (world < 1 || rank < 0 || rank >= world) return fail(MCL_ERR_BAD_ARG, "bad world/rank");
+  // the rank merge packs GLOBAL row ids into the low 32 bits of its sort keys (merge.cu)
+  if (index_base < 0 || index_base + V_local > (1ll << 32))
+    return fail(MCL_ERR_BAD_ARG, "global table rows must stay below 2^32 (index_base %lld + V_local %lld)",
+                (long long)index_base, (long long)V_local);
   const Record rec = record_layout(Q, k);
   const size_t gather_need = mcl_sharded_gather_bytes(Q, k, world);
   if (!gather_buf || gather_bytes < gather_need || !aligned16(gather_buf))
@@ -524,13 +592,89 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
                                      (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "merge launch");
   g_launches++;
-  // 4b. all-gather the merged rows in place
+  // 4b. all-gather the merged rows in place -- unless the caller only consumes its own row range
+  // (host consumers: every rank copies its Q/N rows to the host)
+  if (flags & MCL_SHARDED_LOCAL_ROWS) return MCL_OK;
   nrc = n->group_start();
   if (!nrc) nrc = n->allgather(my_val, topk_val, vb, 0, comm, (cudaStream_t)stream);
   if (!nrc) nrc = n->allgather(my_idx, topk_idx, ib, 0, comm, (cudaStream_t)stream);
   if (!nrc) nrc = n->allgather(my_stats, row_stats, sb, 0, comm, (cudaStream_t)stream);
   const int erc2 = n->group_end();
   if (nrc || erc2) return nccl_fail(n, nrc ? nrc : erc2, "ncclAllGather of the merged rows");
+  return MCL_OK;
+}
+
+// ---- peer exchange of replicated query batches (copy engines over NVLink, no SMs) ----------
+typedef int (*cu_wait32_t)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static cu_wait32_t get_wait32() {
+  static cu_wait32_t fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (cu_wait32_t)p;
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+int mcl_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out) {
+  if (!dev_ptr || !ipc_handle_out || bytes == 0) return fail(MCL_ERR_BAD_ARG, "bad peer_alloc args");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MCL_IPC_HANDLE_BYTES, "ipc handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (peer buffer)");
+  e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return MCL_OK;
+}
+
+int mcl_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return MCL_OK;
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFree (peer buffer)");
+  return MCL_OK;
+}
+
+int mcl_peer_open(const void* ipc_handle, void** peer_ptr) {
+  if (!ipc_handle || !peer_ptr) return fail(MCL_ERR_BAD_ARG, "bad peer_open args");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+  *peer_ptr = p;
+  return MCL_OK;
+}
+
+int mcl_peer_close(void* peer_ptr) {
+  if (!peer_ptr) return MCL_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+  return MCL_OK;
+}
+
+int mcl_memcpy_async(void* dst, const void* src, size_t bytes, mcl_stream_t stream) {
+  if (bytes == 0) return MCL_OK;
+  if (!dst || !src) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync");
+  return MCL_OK;
+}
+
+int mcl_stream_wait_value32(mcl_stream_t stream, const void* dev_addr, uint32_t value) {
+  cu_wait32_t fn = get_wait32();
+  if (!fn) return fail(MCL_ERR_UNIMPLEMENTED, "cuStreamWaitValue32 is not available in this driver");
+  if (!dev_addr || ((uintptr_t)dev_addr & 3u)) return fail(MCL_ERR_BAD_ARG, "bad flag address");
+  const int rc = fn((cudaStream_t)stream, (unsigned long long)(uintptr_t)dev_addr, value, /*GEQ*/ 0u);
+  if (rc) return fail(MCL_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", rc);
   return MCL_OK;
 }
 
@@ -548,6 +692,9 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 10) return g_opt_win.exchange(value);
   if (opt == 11) return g_opt_nosmall.exchange(value);
   if (opt == 12) return g_opt_joint.exchange(value);
+  if (opt == 13) return g_opt_noseed.exchange(value);
+  if (opt == 14) return g_opt_notop1.exchange(value);
+  if (opt == 103) return drift_timeouts_total();
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }

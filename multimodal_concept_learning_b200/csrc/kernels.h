@@ -27,6 +27,10 @@ struct ScanArgs {
   int l2_mode;               // bit 0: query tiles evict-last, bit 1: table tiles evict-first
   float* small_scores;       // small-batch path: [Q][small_ld] score dump, top-k filter off (nullable)
   int64_t small_ld;
+  int mode;                  // epilogue mode of the tcgen05 scan (scan_tc_kernel.cuh): 0 top-k, 1 top-1, 2 seed
+  int tile_stride;           // seed mode: plan tile t = table tile t * tile_stride
+  void* seed_max;            // seed mode: [sample chunks][seed_ld] uint32 keys of the chunk maxima
+  int64_t seed_ld;
 };
 
 // Tile plan of the tcgen05 scan (plan.h).  ctas / gu / cluster = 0: heuristic.  leftover = 0
@@ -54,10 +58,19 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t e
 
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen);
+long long drift_timeouts_total();   // drift waits of the tcgen05 scan that gave up (all devices)
 cudaError_t launch_scan_simt(const ScanArgs& a, const SlotView& sv, int nsplit, cudaStream_t s);
 
 // zero `bytes` (a multiple of 16, 16-byte aligned) on the stream
 cudaError_t launch_zero(void* ptr, size_t bytes, cudaStream_t s);
+
+// seed pre-pass: k-th largest chunk maximum per row -> tau_shared; clears zero_bytes at zero_ptr
+cudaError_t launch_seed_select(const uint32_t* seed_max, int n_chunks, int64_t ld, int64_t rows, int k,
+                               uint32_t* tau_shared, void* zero_ptr, size_t zero_bytes, cudaStream_t s);
+// per-row CE and its mean over the rows with a label from the scan's row statistics
+cudaError_t launch_ce_from_stats(const float* row_stats, const int64_t* labels, int64_t Q,
+                                 float label_smoothing, int64_t vocab, float* loss_rows,
+                                 float* loss_mean, cudaStream_t s);
 
 // slots -> final [Q,k] / [Q,4]
 cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q, int k,

@@ -202,6 +202,57 @@ __global__ void __launch_bounds__(256) zero_words_kernel(uint4* __restrict__ p, 
   if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Threshold seeding (scan_tc_kernel.cuh, kModeSeed): one warp per query row finds the k-th
+// largest of the row's n <= 128 chunk maxima -- k distinct table rows reach it, so it is a lower
+// bound of the row's k-th best score -- by an MSB-first radix descent on the order-preserving
+// keys, and writes it into the row's shared threshold word.  The same launch clears the drift
+// counters and joint words that follow the thresholds in the workspace.
+constexpr int kMaxSeedChunks = 128;
+__global__ void __launch_bounds__(256)
+seed_select_kernel(const uint32_t* __restrict__ seed_max, int n_chunks, long long ld, long long rows,
+                   int k, uint32_t* __restrict__ tau_shared, uint4* __restrict__ zero_ptr, size_t zero_n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n16; i += (size_t)gridDim.x * blockDim.x)
+    zero_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  uint32_t key[kMaxSeedChunks / 32];
+#pragma unroll
+  for (int i = 0; i < kMaxSeedChunks / 32; ++i) {
+    const int c = lane + 32 * i;
+    key[i] = c < n_chunks ? __ldcg(seed_max + (size_t)c * ld + row) : 0u;   // 0 is below every real score
+  }
+  uint32_t prefix = 0u;
+  int kr = k;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t want = (prefix >> bit) | 1u;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxSeedChunks / 32; ++i) c += ((key[i] >> bit) == want) ? 1 : 0;
+    const int tot = __reduce_add_sync(0xffffffffu, c);
+    if (tot >= kr) prefix |= (1u << bit); else kr -= tot;
+  }
+  if (lane == 0) tau_shared[row] = (n_chunks >= k) ? prefix : 0u;
+}
+
+cudaError_t launch_seed_select(const uint32_t* seed_max, int n_chunks, int64_t ld, int64_t rows, int k,
+                               uint32_t* tau_shared, void* zero_ptr, size_t zero_bytes, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  if (n_chunks > kMaxSeedChunks) return cudaErrorInvalidValue;
+  static std::atomic<bool> pref_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !pref_set[dev].load()) {
+    cudaFuncSetAttribute(seed_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    pref_set[dev].store(true);
+  }
+  seed_select_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(seed_max, n_chunks, (long long)ld, (long long)rows, k,
+                                                               tau_shared, (uint4*)zero_ptr, zero_bytes / 16);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_zero(void* ptr, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return cudaSuccess;
   static std::atomic<bool> pref_set[64];

@@ -152,6 +152,59 @@ gather_mean_kernel(const T* __restrict__ table, long long V, int D, long long ld
   }
 }
 
+// Cross-entropy from the scan's row statistics (m, s, sum_z, z_label): per row
+// (1-eps)(lse - z_label) + eps (lse - sum_z / V), 0 on rows whose label is -100, and the mean over
+// the other rows (`F.cross_entropy(..., ignore_index=-100, label_smoothing=eps)`, 'mean').  One
+// block, fixed summation order (deterministic); loss_mean[0] = mean (NaN without a valid row, as
+// torch), loss_mean[1] = number of valid rows.
+__global__ void __launch_bounds__(1024)
+ce_from_stats_kernel(const float4* __restrict__ stats, const long long* __restrict__ labels, long long Q,
+                     float eps, float vocab, float* __restrict__ loss_rows, float* __restrict__ loss_mean) {
+  __shared__ double s_sum[32];
+  __shared__ long long s_cnt[32];
+  double sum = 0.0;
+  long long cnt = 0;
+  for (long long r = threadIdx.x; r < Q; r += blockDim.x) {
+    const float4 st = stats[r];
+    const bool valid = labels[r] != -100;
+    const float lse = st.x + logf(st.y);
+    const float l = valid ? (1.f - eps) * (lse - st.w) + eps * (lse - st.z / vocab) : 0.f;
+    if (loss_rows) loss_rows[r] = l;
+    sum += (double)l;
+    cnt += valid ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
+  __syncthreads();
+  if (warp == 0) {
+    sum = lane < (int)(blockDim.x >> 5) ? s_sum[lane] : 0.0;
+    cnt = lane < (int)(blockDim.x >> 5) ? s_cnt[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+      loss_mean[0] = cnt > 0 ? (float)(sum / (double)cnt) : __int_as_float(0x7fc00000);
+      loss_mean[1] = (float)cnt;
+    }
+  }
+}
+
+cudaError_t launch_ce_from_stats(const float* row_stats, const int64_t* labels, int64_t Q,
+                                 float label_smoothing, int64_t vocab, float* loss_rows,
+                                 float* loss_mean, cudaStream_t s) {
+  ce_from_stats_kernel<<<1, 1024, 0, s>>>((const float4*)row_stats, (const long long*)labels,
+                                          (long long)Q, label_smoothing, (float)vocab,
+                                          loss_rows, loss_mean);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld,
                                 float* out, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;

@@ -147,6 +147,77 @@ __device__ __forceinline__ void row_process_chunk(RowState& st, float (&y)[kChun
   }
 }
 
+// k = 1 specialisation (every training / evaluation call site of the reference is an argmax:
+// multimodal_training.py:276, vision_training.py:132): the row's running maximum IS its top-1,
+// so no candidate buffer, no threshold, no compaction -- st.m holds the best y and st.cnt the
+// table row it came from.  A chunk updates the argmax only when its maximum is strictly larger
+// (columns are visited in increasing order inside a slot: the earliest maximum wins the tie).
+template <bool TAIL, bool CAP>
+__device__ __forceinline__ void row_process_chunk_top1(RowState& st, float (&y)[kChunk], int col0,
+                                                       int n_valid, float a, int lab_local, float rc) {
+  if (TAIL) {
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i)
+      if (i >= n_valid) y[i] = -INFINITY;
+  }
+  float m8[kChunk / 4];
+#pragma unroll
+  for (int h = 0; h < kChunk / 4; ++h)
+    m8[h] = fmaxf(fmaxf(y[4 * h], y[4 * h + 1]), fmaxf(y[4 * h + 2], y[4 * h + 3]));
+  const float cm = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                         fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+  if (lab_local >= col0 && lab_local < col0 + kChunk) {
+    const int off = lab_local - col0;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i)
+      if (i == off) st.y_label = y[i];
+  }
+  if (cm > st.m) {                 // rare after the first tiles: ~ln(columns) times per row
+    int bi = 0;
+#pragma unroll
+    for (int i = kChunk - 1; i >= 0; --i)
+      if (y[i] == cm) bi = i;
+    st.cnt = col0 + bi;
+  }
+  const float m_new = fmaxf(st.m, cm);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!CAP) {
+    const float corr = ex2_fast((st.m - m_new) * a);
+    const float mb = m_new * a;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      acc[i & 3] += ex2_fast(fmaf(y[i], a, -mb));
+      if (TAIL) sy[i & 3] += (i < n_valid) ? y[i] : 0.f; else sy[i & 3] += y[i];
+    }
+    st.s = fmaf(st.s, corr, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+  } else {
+    const float mt_new = tanhf(m_new * rc);
+    const float corr = ex2_fast((tanhf(st.m * rc) - mt_new) * a);
+    const float mb = mt_new * a;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+      const float t = tanhf(y[i] * rc);
+      const float e = ex2_fast(fmaf(t, a, -mb));
+      if (TAIL) { acc[i & 3] += (i < n_valid) ? e : 0.f; sy[i & 3] += (i < n_valid) ? t : 0.f; }
+      else { acc[i & 3] += e; sy[i & 3] += t; }
+    }
+    st.s = fmaf(st.s, corr, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+  }
+  st.m = m_new;
+  st.sum_y += (sy[0] + sy[1]) + (sy[2] + sy[3]);
+}
+
+// Close a k = 1 slot: the argmax is the slot's single candidate, its value the slot's threshold.
+__device__ __forceinline__ void row_flush_top1(RowState& st) {
+  if (st.m > -INFINITY) {
+    st.buf[0] = make_uint2(__float_as_uint(st.m), (uint32_t)st.cnt);
+    st.cnt = 1;
+  } else {
+    st.cnt = 0;
+  }
+  st.tau = st.m;
+}
+
 __device__ __forceinline__ int warp_count_ge(const uint32_t (&key)[kCandCap / 32], uint32_t x) {
   int c = 0;
 #pragma unroll
@@ -228,7 +299,9 @@ __device__ __forceinline__ void warp_compact_rows(RowState& st, int k, uint2* wa
       if (lane == 0 && xj > 1u) atomicMax(joint_warp + (size_t)r * kJointWords, xj);
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
-    uint32_t lo = tau_key + 1u;                        // entries strictly above the threshold
+    // entries AT the threshold count: an entry equal to the row's own tau was appended before tau
+    // rose to its value (earlier table row: it wins the tie) and may be one of the k best
+    uint32_t lo = tau_key;
     uint32_t hi = (mx == 0xffffffffu) ? mx : mx + 1u;  // #{key >= hi} = 0 < k
     uint32_t x = lo;
     int cx = warp_count_ge(key, lo);

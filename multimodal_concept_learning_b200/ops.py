@@ -93,7 +93,7 @@ def _gather_mean_op(table: Tensor, offsets: Tensor, ids: Tensor, normalize: bool
     es = table.element_size()
     ld_out = D + ((-D) % (16 // es))
     buf = torch.empty((Q, ld_out), dtype=table.dtype, device=table.device)
-    flag = torch.zeros(1, dtype=torch.int32, device=table.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=table.device)   # ids were range-checked by gather_mean()
     with torch.cuda.device(table.device):
         check(load().mcl_gather_mean(table.data_ptr(), _dtype_code(table), table.shape[0], D,
                                      table.stride(0), offsets.data_ptr(), ids.data_ptr(), Q,
@@ -106,6 +106,22 @@ def _gather_mean_op(table: Tensor, offsets: Tensor, ids: Tensor, normalize: bool
 @_gather_mean_op.register_fake
 def _(table, offsets, ids, normalize):
     return table.new_empty((offsets.numel() - 1, table.shape[1]))
+
+
+@torch.library.custom_op("mcl::ce_from_stats", mutates_args=(), device_types="cuda")
+def _ce_from_stats_op(stats: Tensor, labels: Tensor, label_smoothing: float, vocab: int) -> Tuple[Tensor, Tensor]:
+    Q = stats.shape[0]
+    rows = torch.empty(Q, dtype=torch.float32, device=stats.device)
+    mean = torch.empty(2, dtype=torch.float32, device=stats.device)
+    with torch.cuda.device(stats.device):
+        check(load().mcl_ce_from_stats(stats.data_ptr(), labels.data_ptr(), Q, float(label_smoothing),
+                                       int(vocab), rows.data_ptr(), mean.data_ptr(), _stream(stats.device)))
+    return rows, mean
+
+
+@_ce_from_stats_op.register_fake
+def _(stats, labels, label_smoothing, vocab):
+    return stats.new_empty(stats.shape[0]), stats.new_empty(2)
 
 
 @torch.library.custom_op("mcl::concept_scan", mutates_args=(), device_types="cuda")
@@ -177,14 +193,28 @@ def row_inv_norm(x: Tensor) -> Tensor:
     return torch.ops.mcl.row_inv_norm(x)
 
 
-def gather_mean(table: Tensor, offsets: Tensor, ids: Tensor, normalize: bool = False) -> Tensor:
-    """CSR gather + mean (+ L2 normalise): multi-token concept embeddings."""
+def gather_mean(table: Tensor, offsets: Tensor, ids: Tensor, normalize: bool = False,
+                validate: bool = True) -> Tensor:
+    """CSR gather + mean (+ L2 normalise): multi-token concept embeddings.
+
+    ``validate`` (default): the CSR arrays are checked before the launch -- ``offsets`` must start
+    at 0, be non-decreasing and end at ``len(ids)``, every id must lie in ``[0, V)`` -- and a bad
+    id raises ``IndexError`` like the reference's ``embedding_matrix[token_ids]``.  Host-built CSR
+    (the shims' ``tokens_to_csr``) is checked on the host for free; device-resident arrays cost one
+    small reduction and a sync, which ``validate=False`` skips (ids are then clamped on the device
+    and the library's bad-id flag is left unread)."""
     dev = _require_cuda(table)
     _dtype_code(table)
-    offsets = offsets.to(device=dev, dtype=torch.int64).contiguous()
-    ids = ids.to(device=dev, dtype=torch.int64).contiguous()
     if offsets.numel() < 1:
         raise ValueError("offsets must have Q+1 entries")
+    if validate:
+        o, i = offsets.to(torch.int64), ids.to(torch.int64)
+        if int(o[0]) != 0 or int(o[-1]) != i.numel() or (o.numel() > 1 and bool((o[1:] < o[:-1]).any())):
+            raise ValueError("offsets must start at 0, be non-decreasing and end at len(ids)")
+        if i.numel() and (int(i.min()) < 0 or int(i.max()) >= table.shape[0]):
+            raise IndexError(f"token id out of range for a table of {table.shape[0]} rows")
+    offsets = offsets.to(device=dev, dtype=torch.int64).contiguous()
+    ids = ids.to(device=dev, dtype=torch.int64).contiguous()
     return torch.ops.mcl.gather_mean(table, offsets, ids, bool(normalize))
 
 
@@ -196,26 +226,30 @@ class ScanOutput:
     vocab: int                  # V the loss normalises label smoothing by
     labels: Optional[Tensor] = None
     label_smoothing: float = 0.0
+    _ce: Optional[Tuple[Tensor, Tensor]] = None
 
     @property
     def lse(self) -> Tensor:
         return self.stats[:, 0] + torch.log(self.stats[:, 1])
 
+    def _cross_entropy(self) -> Tuple[Tensor, Tensor]:
+        """ONE library launch (``mcl_ce_from_stats``) for the per-row losses and their mean."""
+        if self.labels is None:
+            raise ValueError("scan was run without labels")
+        if self._ce is None:
+            self._ce = torch.ops.mcl.ce_from_stats(self.stats, self.labels, float(self.label_smoothing),
+                                                   int(self.vocab))
+        return self._ce
+
     @property
     def loss_rows(self) -> Tensor:
         """Per-row CE, 0 on ignored rows: (1-e)(lse - z_y) + e(lse - sum_z/V)."""
-        if self.labels is None:
-            raise ValueError("scan was run without labels")
-        e = self.label_smoothing
-        lse = self.lse
-        rows = (1.0 - e) * (lse - self.stats[:, 3]) + e * (lse - self.stats[:, 2] / self.vocab)
-        return torch.where(self.labels != IGNORE_INDEX, rows, torch.zeros_like(rows))
+        return self._cross_entropy()[0]
 
     @property
     def loss(self) -> Tensor:
-        """Mean over rows whose label is not -100 (``F.cross_entropy`` 'mean')."""
-        n = (self.labels != IGNORE_INDEX).sum()
-        return self.loss_rows.sum() / n
+        """Mean over rows whose label is not -100 (``F.cross_entropy`` 'mean'; NaN if none)."""
+        return self._cross_entropy()[1][0]
 
 
 def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
@@ -250,9 +284,15 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
         if inv_norm_t.data_ptr() % 16:
             inv_norm_t = inv_norm_t.clone()
     if labels is not None:
-        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
         if labels.shape != (q.shape[0],):
             raise ValueError(f"labels must have shape [{q.shape[0]}]")
+        if not labels.is_cuda and labels.numel() and (vocab_total is not None or index_base == 0):
+            # host labels are range-checked for free; device labels are not (no sync): a label
+            # outside [0, V) other than -100 then contributes z_label = 0 to its row's loss
+            bad = (labels != IGNORE_INDEX) & ((labels < 0) | (labels >= int(vocab_total or table.shape[0])))
+            if bool(bad.any()):
+                raise IndexError("label out of range (labels are global table rows, -100 = ignore)")
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
     if softcap is not None and not softcap > 0:
         raise ValueError("softcap must be > 0 (or None)")
     val, idx, stats = torch.ops.mcl.concept_scan(q, table, inv_norm_q, inv_norm_t, labels,

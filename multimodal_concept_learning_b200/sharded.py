@@ -67,11 +67,18 @@ class ShardedConceptScan:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.vocab_total = int(vocab_total)
         self.lo, self.hi = shard_rows(self.vocab_total, self.world, self.rank)
+        # Rank-independent checks first: an exception on ONE rank before a collective would leave
+        # the others blocked in it.  The shortest shard is the last one.
+        self.min_rows = min(h - l for l, h in (shard_rows(self.vocab_total, self.world, r)
+                                               for r in range(self.world)))
+        if self.min_rows < 1:
+            raise ValueError(f"{self.vocab_total} table rows leave a rank of {self.world} without rows: "
+                             "use fewer ranks")
+        if self.vocab_total > (1 << 32):
+            raise ValueError("the rank merge packs global table rows into 32 bits: vocab_total <= 2^32")
         if table_shard.shape[0] != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} expects rows [{self.lo},{self.hi}) "
                              f"= {self.hi - self.lo}, got {table_shard.shape[0]}")
-        if self.hi - self.lo < 1:
-            raise ValueError("empty table shard: use fewer ranks than table rows / k")
         self.table = ops._rowmajor(table_shard)
         self.device = table_shard.device
         self.inv_norm_t = ops.row_inv_norm(self.table) if normalize_t else None
@@ -106,18 +113,29 @@ class ShardedConceptScan:
             check(load().mcl_comm_all_gather(self._comm, buf.data_ptr() + self.rank * per, buf.data_ptr(), per,
                                              ops._stream(self.device)))
 
+    def local_rows(self, Q: int) -> Tuple[int, int]:
+        """The query rows this rank merges itself under the row exchange (world > 2 and
+        Q % world == 0); every row otherwise."""
+        if self.world > 2 and Q % self.world == 0:
+            per = Q // self.world
+            return self.rank * per, (self.rank + 1) * per
+        return 0, Q
+
     def scan(self, q: Tensor, k: int, *, normalize_q: bool = True, scale: float = 1.0,
              labels: Optional[Tensor] = None, label_smoothing: float = 0.0,
-             inv_norm_q: Optional[Tensor] = None) -> ops.ScanOutput:
+             inv_norm_q: Optional[Tensor] = None, local_rows_only: bool = False) -> ops.ScanOutput:
         """Every rank passes the same ``q`` (and labels, GLOBAL row ids) and receives the same
-        merged answer."""
+        merged answer.  ``local_rows_only``: only the rows of :meth:`local_rows` are valid in the
+        outputs (the final all-gather of the merged rows is skipped) -- for consumers that take
+        each rank's row range separately, e.g. one host copy of 1/world of the result per rank."""
         lib = load()
         dev = self.device
         if not q.is_cuda or q.dtype != self.table.dtype:
             raise TypeError("q must be a CUDA tensor of the table's dtype")
         kk = int(k)
-        if not 1 <= kk <= min(ops.MCL_MAX_K, self.hi - self.lo):
-            raise ValueError(f"k={k} must be in [1, min(rows per shard, {ops.MCL_MAX_K})]")
+        if not 1 <= kk <= min(ops.MCL_MAX_K, self.min_rows):       # the same verdict on every rank
+            raise ValueError(f"k={k} must be in [1, min(rows of the shortest shard = {self.min_rows}, "
+                             f"{ops.MCL_MAX_K})]")
         q = ops._rowmajor(q)
         Q, D = q.shape
         if normalize_q and inv_norm_q is None:
@@ -134,10 +152,124 @@ class ShardedConceptScan:
                 self._gather = torch.empty(gbytes, dtype=torch.uint8, device=dev)
             ws_bytes = lib.mcl_scan_workspace_bytes(Q, self.hi - self.lo, D, kk, code)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            check(lib.mcl_concept_scan_sharded(
+            check(lib.mcl_concept_scan_sharded_ex(
                 q.data_ptr(), self.table.data_ptr(), code, Q, self.hi - self.lo, D, q.stride(0),
                 self.table.stride(0), ops._ptr(inv_norm_q), ops._ptr(self.inv_norm_t), float(scale),
                 kk, self.lo, ops._ptr(labels), val.data_ptr(), idx.data_ptr(), stats.data_ptr(),
                 ws.data_ptr(), ws_bytes, self._gather.data_ptr(), gbytes, self._comm, self.world,
-                self.rank, ops._stream(dev)))
+                self.rank, 1 if local_rows_only else 0, ops._stream(dev)))
         return ops.ScanOutput(val, idx, stats, self.vocab_total, labels, float(label_smoothing))
+
+
+class _RawCudaBuffer:
+    """``__cuda_array_interface__`` view of a raw device pointer (a library-owned or IPC-mapped
+    block), so that torch can alias it without owning it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2}
+
+
+class QueryBoard:
+    """Replicates host-resident query batches on every rank of a sharded scan WITHOUT SMs and
+    without touching the scan's stream order: each rank uploads 1/N of the batch over its own PCIe
+    link into a ring of staging slots and pushes that slice into the same slot of every peer with
+    copy-engine copies over NVLink (CUDA IPC mappings, ``mcl_peer_*``), then writes a step counter
+    into the peer's flag word; the consumer's stream waits for its flag words with a stream memory
+    operation (``mcl_stream_wait_value32``).  All of it runs on a side stream while the previous
+    batch is being scanned.
+
+    Slot reuse needs no back-pressure: every sharded scan ends in a collective over all ranks, so a
+    rank that is enqueueing step n has seen every rank's GPU finish step n - lag - 1 (it holds that
+    step's result on the host); ``slots >= lag + 2`` therefore never overwrites a batch that a peer
+    still reads."""
+
+    def __init__(self, scanner: "ShardedConceptScan", Q: int, D: int, dtype: torch.dtype, slots: int):
+        if scanner.world < 2 or Q % scanner.world:
+            raise ValueError("QueryBoard needs world > 1 and a row count the world size divides")
+        lib = load()
+        self.scanner, self.world, self.rank = scanner, scanner.world, scanner.rank
+        self.Q, self.D, self.dtype, self.slots = int(Q), int(D), dtype, int(slots)
+        self.device = scanner.device
+        es = torch.empty(0, dtype=dtype).element_size()
+        self.rows = self.Q // self.world
+        self.slice_bytes = self.rows * self.D * es
+        self.slot_bytes = self.Q * self.D * es
+        self.flag_off = (self.slots * self.slot_bytes + 255) & ~255
+        self.nbytes = self.flag_off + self.slots * self.world * 4
+        self.step = 0
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(lib.mcl_peer_alloc(self.nbytes, C.byref(ptr), handle))
+        self.base = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=scanner.group)
+        self.peer_base = [None] * self.world
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.peer_base[r] = self.base
+                else:
+                    pp = C.c_void_p()
+                    check(lib.mcl_peer_open(h, C.byref(pp)))
+                    self.peer_base[r] = pp.value
+        self._holder = _RawCudaBuffer(self.base, self.nbytes)
+        raw = torch.as_tensor(self._holder, device=self.device)
+        self.batches = [raw[s * self.slot_bytes:(s + 1) * self.slot_bytes].view(dtype).view(self.Q, self.D)
+                        for s in range(self.slots)]
+        # step counters the flag copies read (pinned host ring, rewritten long after its copy ran)
+        self.vals = torch.zeros(256, dtype=torch.int32).pin_memory()
+        dist.barrier(group=scanner.group)           # every mapping exists before the first push
+
+    def publish(self, host_q: Tensor, copy_stream: torch.cuda.Stream):
+        """Enqueue on ``copy_stream``: upload this rank's row slice of ``host_q`` and push it (and the
+        step counter) to every peer.  Returns (step, event after the local upload)."""
+        lib = load()
+        n = self.step
+        self.step += 1
+        slot = n % self.slots
+        lo = self.rank * self.rows
+        mine = self.batches[slot][lo:lo + self.rows]
+        cs = copy_stream.cuda_stream
+        with torch.cuda.device(self.device), torch.cuda.stream(copy_stream):
+            mine.copy_(host_q[lo:lo + self.rows], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(copy_stream)
+            self.vals[n % 256] = n + 1
+            off = slot * self.slot_bytes + lo * self.D * mine.element_size()
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                check(lib.mcl_memcpy_async(self.peer_base[r] + off, self.base + off, self.slice_bytes, cs))
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                flag = self.peer_base[r] + self.flag_off + 4 * (slot * self.world + self.rank)
+                check(lib.mcl_memcpy_async(flag, self.vals.data_ptr() + 4 * (n % 256), 4, cs))
+        return n, up
+
+    def wait(self, n: int, uploaded: torch.cuda.Event, stream: torch.cuda.Stream) -> Tensor:
+        """Make ``stream`` wait until every rank's slice of step ``n`` has landed; returns the batch."""
+        lib = load()
+        slot = n % self.slots
+        stream.wait_event(uploaded)
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r != self.rank:
+                    check(lib.mcl_stream_wait_value32(stream.cuda_stream,
+                                                      self.base + self.flag_off + 4 * (slot * self.world + r), n + 1))
+        return self.batches[slot]
+
+    def close(self):
+        lib = load()
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.scanner.group)      # nobody pushes into a block that is being freed
+        with torch.cuda.device(self.device):
+            for r, p in enumerate(self.peer_base):
+                if r != self.rank and p:
+                    lib.mcl_peer_close(p)
+            self.batches = []
+            lib.mcl_peer_free(self.base)
+        self.base = None

@@ -130,16 +130,23 @@ def concept_scan_ref(q, table, k: int, *, normalize_q=True, normalize_t=True, sc
     return res
 
 
+def prepare_table_ref(table, normalize=True):
+    """Per-table-version work of the composition below (fp32 copy + row normalisation), so that a
+    timing of the per-query-batch step can hoist it the way the GPU path caches 1/||row||."""
+    tf = table.detach().to("cpu").float()
+    return F.normalize(tf, dim=1) if normalize else tf
+
+
 def torch_composition_ref(q, table, k, *, normalize=True, scale=1.0, labels=None,
-                          label_smoothing=0.0):
+                          label_smoothing=0.0, table_prepared=False):
     """The literal PyTorch composition the reference's training loops reduce to
     (F.normalize / @ / topk / cross_entropy), fp32 on CPU.  Used as cpu_baseline and to
-    check ``concept_scan_ref`` against library kernels rather than against itself."""
+    check ``concept_scan_ref`` against library kernels rather than against itself.
+    ``table_prepared``: ``table`` is the output of :func:`prepare_table_ref`."""
     qf = q.detach().to("cpu").float()
-    tf = table.detach().to("cpu").float()
     if normalize:
         qf = F.normalize(qf, dim=1)
-        tf = F.normalize(tf, dim=1)
+    tf = table if table_prepared else prepare_table_ref(table, normalize)
     z = (qf @ tf.T) * scale
     val, idx = torch.topk(z, k, dim=1)
     out = {"topk_val": val, "topk_idx": idx, "lse": torch.logsumexp(z, dim=1)}

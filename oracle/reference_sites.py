@@ -65,6 +65,20 @@ def color_embedding_correlation_loop_ref(embeddings_by_epoch, ood_tokens, regula
     return np.corrcoef(cd, ed)[0, 1], cd, ed                              # :253
 
 
+def pairwise_cosine_distance_sklearn_loop(token_embeddings: np.ndarray) -> np.ndarray:
+    """The reference's LITERAL hot loop, token_embedding_analysis.py:237-246: one
+    ``sklearn.metrics.pairwise.cosine_similarity([a], [b])`` call per pair i < j.  Returns the
+    embedding distances in loop order.  (bench.py times it as the C1 CPU baseline.)"""
+    from sklearn.metrics.pairwise import cosine_similarity
+    n = len(token_embeddings)
+    out = []
+    for i in range(n):
+        for j in range(i + 1, n):
+            cos_sim = cosine_similarity([token_embeddings[i]], [token_embeddings[j]])[0][0]   # :244
+            out.append(1 - cos_sim)                                                           # :245
+    return np.array(out)
+
+
 def color_embedding_correlation_batched_ref(embeddings_by_epoch, ood_tokens, regular_tokens,
                                             ood_token_ids, regular_token_ids, labels_mapping):
     """Same quantity from ONE n x n cosine matrix -- the formulation the CUDA shim uses

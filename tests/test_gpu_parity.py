@@ -454,3 +454,188 @@ def test_all_labels_ignored_and_out_of_shard(mcl):
     out2 = mcl.concept_scan(q.cuda(), t.cuda(), 20, labels=far, index_base=1000)
     assert (out2.stats[:, 3] == 0).all()
     assert torch.equal(out2.topk_idx, out.topk_idx + 1000)
+
+
+# ---- round 2: k = 1 epilogue, threshold seeding, fused CE, validation -----------------------
+@pytest.mark.parametrize("Q,V,D,cap", [(209, 4104, 1152, None), (700, 3000, 64, None), (24, 9000, 128, None),
+                                       (300, 2500, 72, 8.0), (1, 300, 8, None)])
+def test_top1_epilogue_equals_general_path_and_oracle(mcl, Q, V, D, cap):
+    """k = 1 runs the running-argmax epilogue (no candidate buffers); option 14 sends it through
+    the general top-k filter.  Same scores, same tie rule -> bit-identical outputs; and both match
+    the oracle (raw dot-product logits + CE, the a4 / a5 / a7 call sites)."""
+    q, t = make_inputs(Q, V, D, 100 + Q, dist="aniso" if D == 1152 else "normal")
+    t[V // 2] = t[5]                                  # exact duplicate rows: the lower row must win
+    t[V - 1] = t[5]
+    labels = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(Q))
+    labels[::5] = -100
+    kw = dict(normalize_q=False, normalize_t=False, labels=labels, label_smoothing=0.1, softcap=cap)
+    qd, td = q.cuda(), t.cuda()
+    a = mcl.concept_scan(qd, td, 1, **kw)
+    old = mcl.set_option(14, 1)
+    try:
+        b = mcl.concept_scan(qd, td, 1, **kw)
+    finally:
+        mcl.set_option(14, old)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+    torch.testing.assert_close(a.stats, b.stats, rtol=1e-6, atol=1e-6)
+    ref = R.concept_scan_ref(q, t, 1, normalize_q=False, normalize_t=False, labels=labels,
+                             label_smoothing=0.1, softcap=cap, keep_scores=True)
+    check_topk(a.topk_val, a.topk_idx, ref.scores, 1, rtol=RTOL, atol=1e-4)
+    check_stats(a.stats, ref, rtol=RTOL, atol=1e-3)
+    torch.testing.assert_close(a.loss.cpu().double(), ref.loss.double(), rtol=RTOL, atol=1e-5)
+    # first-max-wins, as torch.argmax / torch.max
+    want = ref.scores.argmax(dim=1)
+    same = a.topk_idx[:, 0].cpu() == want
+    gap = ref.scores.gather(1, want[:, None])[:, 0] - ref.scores.gather(1, a.topk_idx[:, :1].cpu())[:, 0]
+    assert (same | (gap.abs() < 1e-3)).all()
+
+
+def test_top1_gemma3_vocab_shape(mcl):
+    """The reference's real LM head (mllm.py:115 at batch 8): hidden [1672, 1152] x table
+    [262235, 1152] (V % 256 = 91), raw dot product, labels on a few rows, k = 1.  Planted exact
+    copies of table rows must be their own argmax; a row subsample is checked against torch fp32
+    (top-1, log-sum-exp, z_label) and the loss against the same subsample's F.cross_entropy."""
+    Q, V, D = 1672, 262235, 1152
+    g = torch.Generator(device="cuda").manual_seed(2620)
+    t = (torch.randn(V, D, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    q = (torch.randn(Q, D, generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    plant = torch.tensor([0, 90, 255, 256, 131072, V - 92, V - 91, V - 1], device="cuda")
+    q[:8] = t[plant] * 8                                        # <t_j, 8 t_j> dominates every other row
+    labels = torch.full((Q,), -100, dtype=torch.long, device="cuda")
+    lab_rows = torch.arange(3, Q, 67, device="cuda")
+    labels[lab_rows] = torch.randint(0, V, (lab_rows.numel(),), generator=g, device="cuda")
+    labels[:8] = plant
+    out = mcl.concept_scan(q, t, 1, normalize_q=False, normalize_t=False, labels=labels)
+    assert torch.equal(out.topk_idx[:8, 0], plant)
+    sub = torch.cat([torch.arange(0, 8, device="cuda"), lab_rows[:40], torch.arange(Q - 16, Q, device="cuda")])
+    z = q[sub].float() @ t.float().T
+    check_topk(out.topk_val[sub], out.topk_idx[sub], z, 1, rtol=RTOL, atol=1e-4)
+    torch.testing.assert_close(out.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4)
+    has = labels[sub] != -100
+    torch.testing.assert_close(out.stats[sub, 3][has], z[has, labels[sub][has]], rtol=RTOL, atol=1e-4)
+    sel = torch.cat([torch.arange(0, 8, device="cuda"), lab_rows])
+    zl = q[sel].float() @ t.float().T
+    want = torch.nn.functional.cross_entropy(zl, labels[sel])
+    torch.testing.assert_close(out.loss, want, rtol=RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("Q,V,D,k,scale", [(300, 41000, 128, 50, 30.0), (130, 10500, 64, 10, 1.0),
+                                           (4096, 49408, 768, 50, 100.0)])
+def test_threshold_seeding_changes_nothing(mcl, Q, V, D, k, scale):
+    """The seeding pre-pass only tightens the start threshold of every slot's top-k filter: the
+    outputs must be bit-identical with it on and off (option 13), and match the oracle."""
+    from multimodal_concept_learning_b200 import _lib
+    q, t = make_inputs(Q, V, D, 200 + Q)
+    t[V - 3] = t[7]                                    # exact duplicate: tie rule across the seed bound
+    labels = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(Q))
+    qd, td = q.cuda(), t.cuda()
+    n0 = mcl.launch_count()
+    a = mcl.concept_scan(qd, td, k, scale=scale, labels=labels)
+    torch.cuda.synchronize()
+    assert mcl.launch_count() - n0 == 6, "row norms x2, seed scan, seed select, scan, merge"
+    old = mcl.set_option(13, 1)
+    try:
+        b = mcl.concept_scan(qd, td, k, scale=scale, labels=labels)
+    finally:
+        mcl.set_option(13, old)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+    assert torch.equal(a.stats, b.stats)
+    if Q * V <= 20_000_000:
+        ref = R.concept_scan_ref(q, t, k, scale=scale, labels=labels, keep_scores=True)
+        check_topk(a.topk_val, a.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-5 * scale)
+        check_stats(a.stats, ref, rtol=RTOL, atol=1e-4 * scale)
+
+
+def test_seeding_adversarial_sorted_table(mcl):
+    """Sample tiles that are unrepresentative (table sorted by score, ascending and descending)
+    give a weak or a very tight bound -- never a wrong answer."""
+    D, V, k = 64, 45000, 50
+    base = torch.zeros(1, D)
+    base[0, 0] = 1.0
+    ramp = torch.linspace(0.01, 1.0, V)
+    for vals in (ramp, ramp.flip(0)):
+        t = (base * vals[:, None]).to(torch.bfloat16)
+        q = base.repeat(140, 1).to(torch.bfloat16)
+        run_case(mcl, q, t, k, normalize=False, exact=True)
+
+
+def test_k64_many_exact_ties_at_the_threshold(mcl):
+    """More exact ties at the k-th value than a candidate buffer has room for, followed by a few
+    better scores: the compaction must keep the earliest ties (entries equal to the
+    row's own threshold)."""
+    D, V, k = 64, 9000, 64
+    t = torch.zeros(V, D)
+    t[:, 0] = 1.0                                      # 9000 exact ties ...
+    better = torch.tensor([300, 2000, 4100, 4101, 7000, 8999])
+    t[better, 0] = torch.tensor([2.0, 3.0, 2.0, 4.0, 2.0, 5.0])
+    q = torch.zeros(130, D)
+    q[:, 0] = 1.0
+    out = mcl.concept_scan(q.bfloat16().cuda(), t.bfloat16().cuda(), k, normalize_q=False, normalize_t=False)
+    sc = t[:, 0].double()
+    order = sorted(range(V), key=lambda c: (-sc[c].item(), c))[:k]
+    assert out.topk_idx[0].cpu().tolist() == order and out.topk_idx[129].cpu().tolist() == order
+    torch.testing.assert_close(out.topk_val[0].cpu().double(), sc[order], rtol=0, atol=0)
+
+
+def test_fused_ce_kernel_matches_torch(mcl):
+    g = torch.Generator().manual_seed(5)
+    Q, V = 3000, 777
+    z = torch.randn(Q, V, generator=g) * 3
+    labels = torch.randint(0, V, (Q,), generator=g)
+    labels[::3] = -100
+    m = z.max(1).values
+    stats = torch.stack([m, torch.exp(z - m[:, None]).sum(1), z.sum(1),
+                         torch.where(labels >= 0, z.gather(1, labels.clamp_min(0)[:, None])[:, 0], torch.zeros(Q))], 1)
+    for eps in (0.0, 0.1):
+        rows, mean = torch.ops.mcl.ce_from_stats(stats.cuda(), labels.cuda(), eps, V)
+        want_rows = torch.nn.functional.cross_entropy(z, labels, reduction="none", label_smoothing=eps)
+        torch.testing.assert_close(rows.cpu(), want_rows, rtol=1e-5, atol=1e-5)
+        want = torch.nn.functional.cross_entropy(z, labels, label_smoothing=eps)
+        torch.testing.assert_close(mean[0].cpu(), want, rtol=1e-6, atol=1e-6)
+        assert int(mean[1]) == int((labels != -100).sum())
+
+
+def test_scan_loss_is_one_library_launch(mcl):
+    q, t = make_inputs(300, 5000, 64, 91)
+    labels = torch.randint(0, 5000, (300,))
+    out = mcl.concept_scan(q.cuda(), t.cuda(), 5, labels=labels)
+    n0 = mcl.launch_count()
+    loss, rows = out.loss, out.loss_rows
+    assert mcl.launch_count() - n0 == 1 and rows.shape == (300,)
+    torch.testing.assert_close(loss, rows.sum() / 300, rtol=1e-6, atol=1e-6)
+
+
+def test_input_validation_raises_like_the_reference(mcl):
+    table = torch.randn(50, 64).bfloat16().cuda()
+    with pytest.raises(IndexError):                    # embedding_matrix[ids] raises in the reference
+        mcl.gather_mean(table, torch.tensor([0, 2]), torch.tensor([3, 50]))
+    with pytest.raises(ValueError):
+        mcl.gather_mean(table, torch.tensor([0, 3]), torch.tensor([3, 4]))       # offsets end past ids
+    with pytest.raises(ValueError):
+        mcl.gather_mean(table, torch.tensor([0, 2, 1, 2]), torch.tensor([3, 4]))  # not monotone
+    with pytest.raises(IndexError):                    # F.cross_entropy rejects labels >= V
+        mcl.concept_scan(table[:10], table, 1, labels=torch.full((10,), 50))
+    with pytest.raises(IndexError):
+        mcl.gather_mean(table, torch.tensor([0, 1]).cuda(), torch.tensor([-1]).cuda())
+
+
+def test_pipeline_result_lifetime_with_reused_host_buffers(mcl):
+    """with reuse_host_buffers a yielded result stays valid until lag + 1 more results
+    have been yielded."""
+    from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
+    _, t = make_inputs(1, 3000, 64, 92)
+    td = t.cuda()
+    lag = 2
+    pipe = HostQueryPipeline(td, 10, lag=lag, reuse_host_buffers=True)
+    batches = [make_inputs(200, 1, 64, 300 + i)[0].pin_memory() for i in range(12)]
+    held = []
+    for i, res in enumerate(pipe.run(batches)):
+        held.append((i, res, tuple(x.clone() for x in res)))
+        torch.cuda.synchronize()                       # every copy enqueued so far has landed
+        for j, live, snap in held:
+            if i - j <= lag + 1:
+                assert all(torch.equal(a, b) for a, b in zip(live, snap)), f"result {j} overwritten at {i}"
+    assert len(held) == 12
+    for j, _, snap in held[:3]:
+        want = mcl.concept_scan(batches[j].cuda(), td, 10)
+        assert torch.equal(snap[1], want.topk_idx.cpu())

@@ -16,9 +16,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _inputs():
+def _inputs(Q=304):
     g = torch.Generator().manual_seed(77)
-    Q, V, D, k = 300, 6001, 256, 50                 # V odd: ragged shards
+    V, D, k = 6001, 256, 50                         # V odd: ragged shards; 304 = 8 * 38 rows
     q = torch.randn(Q, D, generator=g).to(torch.bfloat16)
     t = torch.randn(V, D, generator=g).to(torch.bfloat16)
     t[4000:4020] = t[:20]                           # exact ties across the shard boundary
@@ -47,8 +47,19 @@ def _worker(rank, world, port, ret):
         assert torch.equal(out.topk_val, full.topk_val), "sharded values differ"
         torch.testing.assert_close(out.lse, full.lse, rtol=1e-6, atol=1e-5)
         torch.testing.assert_close(out.loss, full.loss, rtol=1e-6, atol=1e-6)
+        # a row count the world size does not divide: the all-gather merge instead of the row exchange
+        q2, _, labels2, _ = _inputs(301)
+        out2 = sc.scan(q2.cuda(), k, scale=20.0, labels=labels2.cuda())
+        full2 = mcl.concept_scan(q2.cuda(), td, k, scale=20.0, labels=labels2.cuda())
+        assert torch.equal(out2.topk_idx, full2.topk_idx) and torch.equal(out2.topk_val, full2.topk_val)
+        torch.testing.assert_close(out2.lse, full2.lse, rtol=1e-6, atol=1e-5)
+        # k = 1 (running-argmax epilogue) through the sharded path
+        out3 = sc.scan(qd, 1, normalize_q=False, labels=ld)
+        full3 = mcl.concept_scan(qd, td, 1, normalize_q=False, inv_norm_t=mcl.row_inv_norm(td), labels=ld)
+        assert torch.equal(out3.topk_idx, full3.topk_idx)
+        torch.testing.assert_close(out3.loss, full3.loss, rtol=1e-6, atol=1e-6)
         # host batches through the streaming pipeline: each rank uploads 1/world of the rows and
-        # the library all-gathers them (Q = 300 rows divides by 2 and 4)
+        # the library all-gathers them (Q = 304 rows divides by 2, 4 and 8)
         from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
         pipe = HostQueryPipeline(td[lo:hi], k, scale=20.0, scanner=sc)
         qh = q.pin_memory()
@@ -56,6 +67,20 @@ def _worker(rank, world, port, ret):
         assert len(got) == 3
         assert torch.equal(got[0][1], full.topk_idx.cpu()) and torch.equal(got[2][0], full.topk_val.cpu())
         assert torch.equal(got[1][1], full.topk_idx.cpu().flip(0)), "second (row-reversed) batch differs"
+        pipe.close()
+        # every rank keeps only the rows it merged: 1/world of the result per rank, no final all-gather;
+        # more batches than staging slots, so the slot ring wraps
+        pipe = HostQueryPipeline(td[lo:hi], k, scale=20.0, scanner=sc, local_rows=True, lag=2)
+        r0, r1 = pipe.row_range(qh.shape[0])
+        assert (r0, r1) == ((rank * 304 // world, (rank + 1) * 304 // world) if world > 2 else (0, 304))
+        flipped = qh.flip(0).contiguous().pin_memory()
+        got = list(pipe.run([qh, flipped] * 6))
+        assert len(got) == 12
+        for i, (v, ix, st) in enumerate(got):
+            want_idx = full.topk_idx.cpu() if i % 2 == 0 else full.topk_idx.cpu().flip(0)
+            want_val = full.topk_val.cpu() if i % 2 == 0 else full.topk_val.cpu().flip(0)
+            assert torch.equal(ix, want_idx[r0:r1]) and torch.equal(v, want_val[r0:r1]), f"batch {i}"
+        pipe.close()
         sc.close()
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
@@ -75,7 +100,7 @@ def test_world1_sharded_equals_plain(lib_built):
     torch.testing.assert_close(out.stats, full.stats, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("world", [2, 4])      # 2: all-gather merge; 4: row-exchange merge
+@pytest.mark.parametrize("world", [2, 4, 8])   # 2: all-gather merge; 4, 8: row-exchange merge
 def test_multi_rank_nccl_sharded_equals_unsharded(lib_built, world):
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
