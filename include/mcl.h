@@ -264,7 +264,9 @@ int mcl_stream_wait_value32(mcl_stream_t stream, const void* dev_addr, uint32_t 
  * 11 = 1 sends one-row-block batches through the streaming top-k path instead of the score-dump +
  * radix-select path (tests, A/B), 12 = 1 turns the joint threshold of a row's slots on (rowstate.cuh; measured: +3 % on C2,
  * -3..-6 % elsewhere, so off by default), 13 = 1 turns the threshold-seeding pre-pass off, 14 = 1 sends
- * k = 1 scans through the general top-k epilogue instead of the running-argmax one (tests, A/B);
+ * k = 1 scans through the general top-k epilogue instead of the running-argmax one (tests, A/B),
+ * 15 = what the planner charges a segment's restart in mcl_plan_* (0 = cold top-k filter, 1 = seeded
+ * thresholds, 2 = no filter: k = 1 and the seed pass; the scans choose it themselves per call);
  * opt 100..102 read the last memset / scan / merge
  * time in ns; opt 103 reads how many drift waits of the scan kernel timed out (group members
  * that lost L2 locality because a peer CTA was not resident) since the process started.

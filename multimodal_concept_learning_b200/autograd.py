@@ -81,9 +81,12 @@ class FusedScanCrossEntropy(torch.autograd.Function):
 
 
 def fused_cross_entropy(q: torch.Tensor, table: torch.Tensor, labels: torch.Tensor, *,
-                        scale: float = 1.0, label_smoothing: float = 0.0, chunk_rows: int = 32768):
+                        scale: float = 1.0, label_smoothing: float = 0.0, chunk_rows: int = 32768,
+                        softcap: Optional[float] = None):
     """Differentiable (w.r.t. ``q`` and ``table``) mean cross-entropy of ``scale * q @ table.T``
     against ``labels`` (``-100`` ignored); also returns the row-wise argmax.  ``q`` [Q,D] and
     ``table`` [V,D] are CUDA bf16/fp32 tensors of the same dtype."""
     labels = labels.to(device=q.device, dtype=torch.int64)
+    if softcap:
+        raise NotImplementedError("backward through soft-capped logits is not built yet")
     return FusedScanCrossEntropy.apply(q, table, labels, scale, label_smoothing, chunk_rows)

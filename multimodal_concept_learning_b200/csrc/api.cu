@@ -18,12 +18,13 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
 std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0}, g_opt_joint{0};
-std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0};
+std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0}, g_opt_filter{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
   k.ctas = (int)g_opt_ctas.load(); k.gu = (int)g_opt_g.load(); k.cluster = (int)g_opt_cluster.load();
   k.leftover = (int)g_opt_leftover.load(); k.seg_penalty = (int)g_opt_segpen.load(); k.win = (int)g_opt_win.load();
+  k.filter = (int)g_opt_filter.load();   // plan introspection only: scans pick it per call (scan_layout)
   return k;
 }
 float g_phase_ms[3] = {0.f, 0.f, 0.f};   // last scan: memset, scan kernel, merge kernel (option 6)
@@ -101,11 +102,8 @@ ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int k, int dtype, int sm
   L.tc = use_tc(dtype);
   const int num_rb = (int)((Q + kBlockM - 1) / kBlockM);
   if (L.tc) {
-    L.plan = make_tc_plan(Q, V, D, sm, knobs());
-    L.nslots = plan_nslots(L.plan);
-    L.rows_padded = L.plan.ru * L.plan.cs;
-    L.nctr = plan_nctr(L.plan);
     L.mode = (k == 1 && !g_opt_notop1.load()) ? 1 : 0;
+    const int num_vt = (int)((V + kBlockN - 1) / kBlockN), num_kb = (int)((D + kBlockK - 1) / kBlockK);
     L.small_ld = (V + kChunk - 1) / kChunk * kChunk;
     L.scores_bytes = (((size_t)Q * L.small_ld * sizeof(float)) + 255) & ~(size_t)255;
     // (k = 1 needs no score dump: the running argmax of the top-1 epilogue is the answer)
@@ -113,12 +111,19 @@ ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int k, int dtype, int sm
     // Seeding pays where the epilogue, not the tensor pipe, bounds the scan (D <= 1536) and the
     // sample -- ~2.5 k chunk maxima per row, at most 16 tiles -- is under a tenth of the table.
     const int nt = std::min(16, (5 * k / 2 + 7) / 8);
-    if (!L.small && L.mode == 0 && !g_opt_noseed.load() && L.plan.num_kb <= 24 && nt >= 1 &&
-        nt * 8 >= k && L.plan.num_vt >= 10 * nt) {
-      L.seed = true;
+    L.seed = !L.small && L.mode == 0 && !g_opt_noseed.load() && num_kb <= 24 && nt >= 1 && nt * 8 >= k &&
+             num_vt >= 10 * nt;
+    PlanKnobs kn = knobs();
+    kn.filter = L.mode == 1 ? 2 : (L.seed ? 1 : 0);     // what a segment's restart costs (scan_tc.cu)
+    L.plan = make_tc_plan(Q, V, D, sm, kn);
+    L.nslots = plan_nslots(L.plan);
+    L.rows_padded = L.plan.ru * L.plan.cs;
+    L.nctr = plan_nctr(L.plan);
+    if (L.seed) {
       L.seed_tiles = nt;
       L.seed_stride = (L.plan.num_vt - 1) / nt;          // never the last (ragged) tile
-      L.seed_plan = make_tc_plan(Q, (int64_t)nt * kBlockN, D, sm, knobs());
+      kn.filter = 2;
+      L.seed_plan = make_tc_plan(Q, (int64_t)nt * kBlockN, D, sm, kn);
       L.seed_ld = (int64_t)std::max(L.rows_padded, L.seed_plan.ru * L.seed_plan.cs) * kBlockM;
       L.seed_bytes = (((size_t)nt * (kBlockN / kChunk) * L.seed_ld * sizeof(uint32_t)) + 255) & ~(size_t)255;
       L.extra_bytes = L.seed_bytes;
@@ -694,6 +699,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 12) return g_opt_joint.exchange(value);
   if (opt == 13) return g_opt_noseed.exchange(value);
   if (opt == 14) return g_opt_notop1.exchange(value);
+  if (opt == 15) return g_opt_filter.exchange(value);
   if (opt == 103) return drift_timeouts_total();
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;

@@ -36,7 +36,7 @@ struct ScanArgs {
 // Tile plan of the tcgen05 scan (plan.h).  ctas / gu / cluster = 0: heuristic.  leftover = 0
 // plans without tail workers (A/B measurements); seg_penalty = tiles charged per extra segment
 // of a tail worker when balancing it against the groups.
-struct PlanKnobs { int ctas = 0, gu = 0, cluster = 0, leftover = 1, seg_penalty = 1, win = 0; };
+struct PlanKnobs { int ctas = 0, gu = 0, cluster = 0, leftover = 1, seg_penalty = 1, win = 0, filter = 0; };
 TcPlan make_tc_plan(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKnobs& knobs);
 inline int plan_nslots(const TcPlan& p) { return p.ru * p.cs * p.S * 2; }   // incl. padding row blocks
 inline int plan_nctr(const TcPlan& p) { return p.waves * p.nsync; }

@@ -21,6 +21,14 @@ template <> struct Vec<__nv_bfloat16> {
       f[2 * i] = v.x; f[2 * i + 1] = v.y;
     }
   }
+  __device__ static __forceinline__ void widen(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = __bfloat1622float2(h[i]);
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  }
   __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
     uint4 u;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -36,6 +44,9 @@ template <> struct Vec<float> {
   __device__ static __forceinline__ void load(const float* p, float (&f)[4]) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p));
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static __forceinline__ void widen(const uint4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
   }
   __device__ static __forceinline__ void store(float* p, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
@@ -152,6 +163,83 @@ gather_mean_kernel(const T* __restrict__ table, long long V, int D, long long ld
   }
 }
 
+// Register-resident variant for rows of at most 32 * NV 16-byte vectors (D <= 4096 bf16 with
+// NV = 16): every table row is read ONCE -- the fp32 means stay in registers between the sum, the
+// optional norm and the store, where the generic kernel above re-gathers the rows for its second
+// pass -- and a lane has NV independent 16-byte loads in flight per gathered row (a gather is
+// latency-bound: few warps fit at this register count, so the parallelism has to come from inside
+// the thread).  Same arithmetic, same order: bit-identical outputs.
+template <typename T, int NV>
+__global__ void __launch_bounds__(128)
+gather_mean_reg_kernel(const T* __restrict__ table, long long V, int D, long long ld,
+                       const long long* __restrict__ offsets, const long long* __restrict__ ids,
+                       long long Q, int normalize, T* __restrict__ out, long long ld_out,
+                       int* __restrict__ bad_flag) {
+  constexpr int N = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= Q) return;
+  const long long b = offsets[row], e = offsets[row + 1];
+  const int n = (int)(e - b);
+  const float fn = (float)(n > 0 ? n : 1);
+  const int nvec = D / N;
+  const int ntail = D - nvec * N;                  // < N ragged columns: lane c owns column nvec*N + c
+  T* o = out + row * ld_out;
+  float acc[NV][N];
+  float tail = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int c = 0; c < N; ++c) acc[i][c] = 0.f;
+  for (long long j = b; j < e; ++j) {
+    long long id = __ldg(ids + j);
+    if (id < 0 || id >= V) { if (bad_flag) *bad_flag = 1; id = id < 0 ? 0 : V - 1; }
+    const T* src = table + id * ld;
+    uint4 raw[NV];                                 // all loads of the row first, widened on use
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      raw[i] = (v < nvec) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)v * N)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (lane < ntail) tail += Vec<T>::ld1(src + nvec * N + lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a[N];
+      Vec<T>::widen(raw[i], a);
+#pragma unroll
+      for (int c = 0; c < N; ++c) acc[i][c] += a[c];   // (+0 past nvec)
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      acc[i][c] = acc[i][c] / fn;
+      ss = fmaf(acc[i][c], acc[i][c], ss);         // (vectors past nvec hold zeros)
+    }
+  }
+  tail = tail / fn;
+  float inv = 1.f;
+  if (normalize) {
+    if (lane < ntail) ss = fmaf(tail, tail, ss);
+    const float nrm = sqrtf(warp_sum(ss));
+    inv = (nrm < kTinyNorm) ? 1.0f : 1.0f / nrm;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      if (normalize) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc[i][c] *= inv;
+      }
+      Vec<T>::store(o + (size_t)v * N, acc[i]);
+    }
+  }
+  if (lane < ntail) Vec<T>::st1(o + nvec * N + lane, normalize ? tail * inv : tail);
+}
+
 // Cross-entropy from the scan's row statistics (m, s, sum_z, z_label): per row
 // (1-eps)(lse - z_label) + eps (lse - sum_z / V), 0 on rows whose label is -100, and the mean over
 // the other rows (`F.cross_entropy(..., ignore_index=-100, label_smoothing=eps)`, 'mean').  One
@@ -216,20 +304,36 @@ cudaError_t launch_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t 
   return cudaGetLastError();
 }
 
+template <typename T>
+static void launch_gather_mean_t(const T* table, int64_t V, int64_t D, int64_t ld, const int64_t* offsets,
+                                 const int64_t* ids, int64_t Q, int normalize, T* out, int64_t ld_out,
+                                 int* bad_flag, cudaStream_t s) {
+  const int64_t nvec = D / Vec<T>::N;
+  const unsigned grid4 = (unsigned)((Q + 3) / 4);
+#define MCL_GM_REG(NV)                                                                              \
+  gather_mean_reg_kernel<T, NV><<<grid4, 128, 0, s>>>(table, V, (int)D, ld, (const long long*)offsets, \
+                                                      (const long long*)ids, Q, normalize, out, ld_out, bad_flag)
+  if (nvec <= 32 * 4) MCL_GM_REG(4);
+  else if (nvec <= 32 * 8) MCL_GM_REG(8);
+  else if (nvec <= 32 * 16) MCL_GM_REG(16);
+  else
+    gather_mean_kernel<T><<<(unsigned)((Q + 7) / 8), 256, 0, s>>>(table, V, (int)D, ld, (const long long*)offsets,
+                                                                 (const long long*)ids, Q, normalize, out, ld_out,
+                                                                 bad_flag);
+#undef MCL_GM_REG
+}
+
 cudaError_t launch_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t ld,
                                const int64_t* offsets, const int64_t* ids, int64_t Q,
                                int normalize, void* out, int64_t ld_out, int* bad_flag,
                                cudaStream_t s) {
   if (Q == 0) return cudaSuccess;
-  const unsigned grid = (unsigned)((Q + 7) / 8);
   if (dtype == 0)
-    gather_mean_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
-        (const __nv_bfloat16*)table, V, (int)D, ld, (const long long*)offsets,
-        (const long long*)ids, Q, normalize, (__nv_bfloat16*)out, ld_out, bad_flag);
+    launch_gather_mean_t<__nv_bfloat16>((const __nv_bfloat16*)table, V, D, ld, offsets, ids, Q, normalize,
+                                        (__nv_bfloat16*)out, ld_out, bad_flag, s);
   else
-    gather_mean_kernel<float><<<grid, 256, 0, s>>>(
-        (const float*)table, V, (int)D, ld, (const long long*)offsets, (const long long*)ids, Q,
-        normalize, (float*)out, ld_out, bad_flag);
+    launch_gather_mean_t<float>((const float*)table, V, D, ld, offsets, ids, Q, normalize, (float*)out,
+                                ld_out, bad_flag, s);
   return cudaGetLastError();
 }
 

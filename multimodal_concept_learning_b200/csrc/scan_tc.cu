@@ -107,8 +107,12 @@ static TcPlan make_tc_plan_uncached(int64_t Q, int64_t V, int64_t D, int sm_coun
   // candidate buffers are hot too: ~1 KB per query row, slot and column half
   const double buf_slot = (double)p.cs * 2.0 * kBlockM * 1024.0;
   // restart of the top-k filter per segment, in tiles (see plan_node); option 8 scales it
-  const int cold = std::max(1, (int)(1.5e-4 * kn.seg_penalty / t_tile + 0.5));
-  const int warm = std::max(1, (int)(0.4e-4 * kn.seg_penalty / t_tile + 0.5));
+  // (kn.filter: 0 = the top-k filter starts cold in every slot; 1 = thresholds seeded by the
+  // pre-pass: a segment restarts almost warm; 2 = no filter at all (k = 1 epilogue, seed pass))
+  const double cold_s = kn.filter == 0 ? 1.5e-4 : (kn.filter == 1 ? 0.2e-4 : 0.0);
+  const double warm_s = kn.filter == 0 ? 0.4e-4 : (kn.filter == 1 ? 0.1e-4 : 0.0);
+  const int cold = std::max(1, (int)(cold_s * kn.seg_penalty / t_tile + 0.5));
+  const int warm = std::max(1, (int)(warm_s * kn.seg_penalty / t_tile + 0.5));
   const bool tails = kn.leftover != 0;
   double best = 1e300;
   int best_gu = 1;
@@ -162,7 +166,7 @@ TcPlan make_tc_plan(int64_t Q, int64_t V, int64_t D, int sm_count, const PlanKno
   thread_local int next = 0;
   auto same = [&](const Key& k) {
     return k.Q == Q && k.V == V && k.D == D && k.sm == sm_count && k.kn.ctas == kn.ctas && k.kn.gu == kn.gu &&
-           k.kn.cluster == kn.cluster && k.kn.leftover == kn.leftover && k.kn.seg_penalty == kn.seg_penalty &&
+           k.kn.cluster == kn.cluster && k.kn.leftover == kn.leftover && k.kn.seg_penalty == kn.seg_penalty && k.kn.filter == kn.filter &&
            k.kn.win == kn.win;
   };
   for (const Entry& e : cache)

@@ -49,26 +49,8 @@ def _stub_missing():
             sys.modules[name] = m
 
 
-class ToyTokenizer:
-    """Deterministic word-piece tokenizer: splits on spaces and '-', maps each piece to an
-    id by a fixed hash; unknown/empty text -> []. decode() joins 'yes'/'no'/tokN."""
-
-    def __init__(self, vocab: int, yes_id: int = 7, no_id: int = 11):
-        self.vocab, self.yes_id, self.no_id = vocab, yes_id, no_id
-
-    def encode(self, text, add_special_tokens=False):
-        pieces = [p for p in text.replace("-", " ").split(" ") if p]
-        out = []
-        for p in pieces:
-            h = 0
-            for ch in p:
-                h = (h * 131 + ord(ch)) % 1000003
-            out.append(h % self.vocab)
-        return out
-
-    def decode(self, ids, skip_special_tokens=True):
-        words = {self.yes_id: "yes", self.no_id: "no"}
-        return " ".join(words.get(int(i), f"tok{int(i)}") for i in ids)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from tests.tiny_models import ToyTokenizer, tiny_lm_config, tiny_vit_config  # noqa: E402
 
 
 def color_fixture(seed=0, V=512, D=64):
@@ -126,27 +108,30 @@ def gen_a3():
     print("a3", {k: tuple(v.shape) for k, v in res.items()})
 
 
-def tiny_mllm(seed=2, V=640, H=64):
-    from transformers import Gemma3ForCausalLM, Gemma3TextConfig, ViTConfig, ViTModel
+def tiny_mllm(seed=2):
+    from transformers import Gemma3ForCausalLM, ViTModel
     from src.multimodal.mllm import MLLM
     torch.manual_seed(seed)
-    lm_cfg = Gemma3TextConfig(vocab_size=V, hidden_size=H, intermediate_size=128,
-                              num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
-                              head_dim=16, max_position_embeddings=128, sliding_window=64,
-                              attn_implementation="eager")
-    vit_cfg = ViTConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2,
-                        intermediate_size=64, image_size=32, patch_size=16)  # 4 patches + CLS = 5
     m = MLLM.__new__(MLLM)                 # bypass from_pretrained (no weights offline)
     torch.nn.Module.__init__(m)
     m.vision_model_name = "tiny-vit"
     m.language_model_name = "tiny-gemma3"
     m.num_vision_tokens = 5
-    m.vision_model = ViTModel(vit_cfg)
-    m.language_model = Gemma3ForCausalLM(lm_cfg).to(torch.bfloat16)
-    m.projector = torch.nn.Linear(32, H)
-    m.tokenizer = ToyTokenizer(V)
+    m.vision_model = ViTModel(tiny_vit_config())
+    m.language_model = Gemma3ForCausalLM(tiny_lm_config()).to(torch.bfloat16)
+    m.projector = torch.nn.Linear(32, 64)
+    m.tokenizer = ToyTokenizer(640)
     m.labels_mapping = None
     return m
+
+
+def _state_arrays(module, prefix):
+    """state_dict as npz-able arrays; bf16 tensors are stored as fp32 (exact) + a dtype marker."""
+    out = {}
+    for k, v in module.state_dict().items():
+        out[f"{prefix}{k}"] = v.detach().float().numpy() if v.dtype == torch.bfloat16 else v.detach().numpy()
+        out[f"{prefix}{k}::bf16"] = np.bool_(v.dtype == torch.bfloat16)
+    return out
 
 
 def gen_a4_a5():
@@ -183,6 +168,10 @@ def gen_a4_a5():
     mt.tqdm = lambda it, **kw: it
     with contextlib.redirect_stdout(io.StringIO()):
         ev = mt.evaluate_model(m, [batch], cfg, Acc())
+    # the whole tiny model + the batch, so that the GPU test can run the DROP-IN forward /
+    # evaluate_model (shims.mllm.fused_forward bound as MLLM.forward) end to end
+    np.savez(os.path.join(OUT, "a4_a5_mllm_model.npz"), images=images.numpy(), input_ids=input_ids.numpy(),
+             attention_mask=attention_mask.numpy(), **_state_arrays(m, "sd::"))
     np.savez(os.path.join(OUT, "a4_a5_mllm_head.npz"),
              hidden=hidden["h"].float().numpy(), hidden_is_bf16=np.bool_(hidden["h"].dtype == torch.bfloat16),
              table=table.float().numpy(), labels=labels.numpy(),
@@ -214,12 +203,39 @@ def gen_a7():
     print("a7", out)
 
 
+def gen_a7_model():
+    """vision_training.py:81-83,115-116,132 on a tiny ViTForImageClassification (the class the
+    reference trains from scratch, vision_training.py:259-275): criterion(outputs.logits, labels)
+    and torch.max(outputs.logits.data, 1), under the fp32 the CPU run uses."""
+    from transformers import ViTForImageClassification
+    torch.manual_seed(5)
+    C = 37
+    model = ViTForImageClassification(tiny_vit_config(num_labels=C)).eval()
+    with torch.no_grad():                  # a head that discriminates (HF initialises it near zero)
+        model.classifier.weight.mul_(40.0)
+        model.classifier.bias.normal_(generator=torch.Generator().manual_seed(8))
+    g = torch.Generator().manual_seed(6)
+    images = torch.randn(9, 3, 32, 32, generator=g)
+    labels = torch.randint(0, C, (9,), generator=g)
+    out = {}
+    with torch.no_grad():
+        outputs = model(images)
+        for eps in (0.0, 0.1):
+            criterion = torch.nn.CrossEntropyLoss(label_smoothing=eps) if eps > 0 else torch.nn.CrossEntropyLoss()
+            out[f"loss_{eps}"] = np.float64(criterion(outputs.logits, labels).item())
+        _, predicted = torch.max(outputs.logits.data, 1)
+    np.savez(os.path.join(OUT, "a7_vit_model.npz"), images=images.numpy(), labels=labels.numpy(),
+             logits=outputs.logits.numpy(), predicted=predicted.numpy(), num_labels=C,
+             **out, **_state_arrays(model, "sd::"))
+    print("a7 model", out, predicted.tolist())
+
+
 def main():
     assert os.path.isdir(REF), "reference tree not present: fixtures can only be regenerated in the build container"
     os.makedirs(OUT, exist_ok=True)
     _stub_missing()
     sys.path.insert(0, REF)
-    gen_a1(); gen_a3(); gen_a4_a5(); gen_a7()
+    gen_a1(); gen_a3(); gen_a4_a5(); gen_a7(); gen_a7_model()
 
 
 if __name__ == "__main__":

@@ -199,13 +199,37 @@ def test_plan_fuzz(lib_built):
     @given(Q=st.one_of(st.integers(1, 600), st.integers(1, 40000)),
            V=st.one_of(st.integers(1, 3000), st.integers(1, 400000)),
            D=st.sampled_from([8, 64, 72, 768, 1152, 3584, 4096]),
-           sm=st.one_of(st.integers(1, 12), st.sampled_from([132, 148, 160])))
-    def run(Q, V, D, sm):
+           sm=st.one_of(st.integers(1, 12), st.sampled_from([132, 148, 160])),
+           flt=st.sampled_from([0, 1, 2]))
+    def run(Q, V, D, sm, flt):
         if (-(-Q // 128)) * (-(-V // 256)) > 60000:       # keep the enumeration small
             V = max(1, 60000 * 256 // (-(-Q // 128)))
-        _check_plan(lib, _lib, Q, V, D, sm)
+        old = lib.mcl_set_option(15, flt)                  # restart charge: cold / seeded / no filter
+        try:
+            _check_plan(lib, _lib, Q, V, D, sm)
+        finally:
+            lib.mcl_set_option(15, old)
 
     run()
+
+
+def test_plans_without_a_cold_filter_are_balanced(lib_built):
+    """The seed pass (16 sample tiles) and k = 1 scans have no top-k filter to warm up: their plans
+    must not trade balance for fewer segments (round 2: the seed pass of C2 took 63 us with the
+    cold-filter charges -- 16 tiles on some workers, 2 on others)."""
+    from multimodal_concept_learning_b200 import _lib
+    lib = _lib.load()
+    old = lib.mcl_set_option(15, 2)
+    try:
+        for Q, V, D in [(4096, 4096, 768), (1672, 262235, 1152), (32768, 4096, 1024)]:
+            p = _lib.plan_scan(Q, V, D, 148)
+            per = {}
+            for w, unit, vt0, vt1, j, sync in _lib.plan_segments(Q, V, D, 148):
+                per[w] = per.get(w, 0) + vt1 - vt0
+            ideal = p["ru"] * p["num_vt"] / p["workers"]
+            assert max(per.values()) <= 1.15 * ideal + 1.5, (Q, V, D, max(per.values()), ideal)
+    finally:
+        lib.mcl_set_option(15, old)
 
 
 def test_header_is_plain_c_and_links(lib_built, tmp_path):
