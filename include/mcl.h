@@ -121,6 +121,21 @@ int mcl_concept_scan(const void* q /*[Q,D]*/, const void* table /*[V_local,D]*/,
                      mcl_stream_t stream);
 
 /*
+ * The same scan with every option in one call: softcap (0 = off) as in mcl_concept_scan_softcap,
+ * and flags.  MCL_SCAN_NORMALIZE_Q: inv_norm_q is NULL and the library forms 1/||q_row|| itself
+ * (sklearn zero-row rule) -- inside the scan kernel for batches of up to 64 rows, where launches
+ * bound the step (the reference's 6..96 concept tokens), else with the row kernel into workspace
+ * scratch.  The values are bit-identical to mcl_row_inv_norm's.
+ */
+#define MCL_SCAN_NORMALIZE_Q 1
+int mcl_concept_scan_ex(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
+                        int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                        const float* inv_norm_t, float scale, float softcap, int k,
+                        int64_t index_base, const int64_t* labels, float* topk_val,
+                        int64_t* topk_idx, float* row_stats, void* workspace, size_t workspace_bytes,
+                        int flags, mcl_stream_t stream);
+
+/*
  * Soft-capped variant: every logit is z' = softcap * tanh(z / softcap) before the top-k values,
  * the log-sum-exp, sum_z and z_label are formed (ranking is by z: tanh is monotone).
  * softcap = 0 is mcl_concept_scan.  scores_out is nullable (a [Q,V_local] dump of z' for tests).
@@ -216,6 +231,7 @@ int mcl_concept_scan_sharded(const void* q, const void* table_shard, int dtype, 
  * Without the row exchange every rank merges every row and the flag changes nothing.
  */
 #define MCL_SHARDED_LOCAL_ROWS 1
+#define MCL_SHARDED_NORMALIZE_Q 2   /* inv_norm_q is NULL: the library forms the query norms (MCL_SCAN_NORMALIZE_Q) */
 int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtype, int64_t Q,
                                 int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
                                 const float* inv_norm_q, const float* inv_norm_t, float scale,
@@ -266,7 +282,8 @@ int mcl_stream_wait_value32(mcl_stream_t stream, const void* dev_addr, uint32_t 
  * -3..-6 % elsewhere, so off by default), 13 = 1 turns the threshold-seeding pre-pass off, 14 = 1 sends
  * k = 1 scans through the general top-k epilogue instead of the running-argmax one (tests, A/B),
  * 15 = what the planner charges a segment's restart in mcl_plan_* (0 = cold top-k filter, 1 = seeded
- * thresholds, 2 = no filter: k = 1 and the seed pass; the scans choose it themselves per call);
+ * thresholds, 2 = no filter: k = 1 and the seed pass; the scans choose it themselves per call),
+ * 16 = 1 keeps the query norms of MCL_SCAN_NORMALIZE_Q out of the scan kernel (tests, A/B);
  * opt 100..102 read the last memset / scan / merge
  * time in ns; opt 103 reads how many drift waits of the scan kernel timed out (group members
  * that lost L2 locality because a peer CTA was not resident) since the process started.

@@ -38,6 +38,8 @@ SIGNATURES = {
     "mcl_scan_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "mcl_concept_scan": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32,
                                 _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "mcl_concept_scan_ex": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _f32,
+                                   _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _i32, _ptr]),
     "mcl_concept_scan_softcap": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
                                         _f32, _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz,
                                         _ptr, _ptr]),

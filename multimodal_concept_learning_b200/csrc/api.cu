@@ -18,7 +18,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
 std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0}, g_opt_joint{0};
-std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0}, g_opt_filter{0};
+std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0}, g_opt_filter{0}, g_opt_noqnorm{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
@@ -167,7 +167,7 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
               int64_t ldq, int64_t ldt, const float* inv_q, const float* inv_t, float scale, int k,
               int64_t index_base, const int64_t* labels, float* topk_val, int64_t* topk_idx,
               float* row_stats, void* workspace, size_t workspace_bytes, float* dbg,
-              cudaStream_t stream, float softcap = 0.f) {
+              cudaStream_t stream, float softcap = 0.f, int flags = 0) {
   int rc = check_scan_args(q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, topk_val,
                            topk_idx, row_stats);
   if (rc) return rc;
@@ -180,14 +180,31 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   if (!workspace || workspace_bytes < ws.bytes || !aligned16(workspace))
     return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %zu B (or null/unaligned)",
                 workspace_bytes, ws.bytes);
+  // MCL_SCAN_NORMALIZE_Q: the library forms 1/||q_row|| itself -- inside the scan kernel for small
+  // batches (no extra launch), else with the row kernel into a workspace scratch
+  const bool want_qnorm = (flags & MCL_SCAN_NORMALIZE_Q) && !inv_q;
+  const bool qnorm_in_kernel = want_qnorm && L.tc && dtype == MCL_DTYPE_BF16 && Q <= 64 && !g_opt_noqnorm.load();
+  if (want_qnorm && !qnorm_in_kernel) {
+    cudaError_t e0 = launch_row_inv_norm(q, dtype, Q, D, ldq, ws.inv_q, stream);
+    if (e0 != cudaSuccess) return cuda_fail(e0, "row_inv_norm launch (queries)");
+    g_launches++;
+  }
+  if (want_qnorm) inv_q = ws.inv_q;                 // (the merge reads what the scan kernel published)
   ScanArgs a{q, table, dtype, Q, V, D, ldq, ldt, inv_q, inv_t, scale, k, index_base, labels, dbg,
              g_opt_timing.load() ? ws.timing : nullptr, ws.tau_shared, ws.sync_ctr,
              g_opt_joint.load() ? ws.joint : nullptr, softcap,
-             (int)g_opt_l2.load(), nullptr, 0, L.mode, 1, nullptr, 0};
+             (int)g_opt_l2.load(), nullptr, 0, L.mode, 1, nullptr, 0,
+             qnorm_in_kernel ? 1 : 0, ws.inv_q, nullptr, 0};
   // Small batches (one row block) without a caller-side score dump: the scan keeps only the
   // statistics and drops the scores into the workspace; select.cu picks the top-k from them.
   const bool small = L.small && !dbg;
-  if (small) { a.small_scores = (float*)ws.extra; a.small_ld = L.small_ld; }
+  if (small) {
+    a.small_scores = (float*)ws.extra; a.small_ld = L.small_ld;
+    // the selection kernel counts range arrivals per row in the (otherwise unused) threshold words:
+    // the scan kernel zeroes them, so this path needs no clear launch
+    a.tau_shared = nullptr;
+    a.clear_words = ws.tau_shared; a.n_clear = (int)(L.rows_padded * kBlockM);
+  }
   SlotMap map{};
   cudaError_t e;
   const bool phases = g_opt_phase.load() != 0;
@@ -212,8 +229,9 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
                              ws.zero_bytes - ((char*)ws.sync_ctr - (char*)ws.tau_shared), stream);
       if (e != cudaSuccess) return cuda_fail(e, "seed select launch");
       g_launches++;
-    } else if (L.mode == 0 || L.plan.ru > 1) {
-      // (a k = 1 scan of a single row unit reads neither thresholds nor drift counters)
+    } else if (!small && (L.mode == 0 || L.plan.ru > 1)) {
+      // (a k = 1 scan of a single row unit reads neither thresholds nor drift counters; neither
+      // does the small-batch path)
       e = launch_zero(ws.tau_shared, ws.zero_bytes, stream);
       if (e != cudaSuccess) return cuda_fail(e, "clearing the shared thresholds");
       g_launches++;
@@ -380,6 +398,16 @@ int mcl_concept_scan(const void* q, const void* table, int dtype, int64_t Q, int
                    nullptr, (cudaStream_t)stream);
 }
 
+int mcl_concept_scan_ex(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
+                        int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
+                        const float* inv_norm_t, float scale, float softcap, int k, int64_t index_base,
+                        const int64_t* labels, float* topk_val, int64_t* topk_idx, float* row_stats,
+                        void* workspace, size_t workspace_bytes, int flags, mcl_stream_t stream) {
+  return scan_impl(q, table, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, k,
+                   index_base, labels, topk_val, topk_idx, row_stats, workspace, workspace_bytes,
+                   nullptr, (cudaStream_t)stream, softcap, flags);
+}
+
 int mcl_concept_scan_softcap(const void* q, const void* table, int dtype, int64_t Q, int64_t V_local,
                              int64_t D, int64_t ldq, int64_t ldt, const float* inv_norm_q,
                              const float* inv_norm_t, float scale, float softcap, int k,
@@ -537,7 +565,8 @@ int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtyp
   int rc = scan_impl(q, table_shard, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale,
                      k, index_base, labels, (float*)(mine + rec.val_off),
                      (int64_t*)(mine + rec.idx_off), (float*)(mine + rec.stats_off), workspace,
-                     workspace_bytes, nullptr, (cudaStream_t)stream);
+                     workspace_bytes, nullptr, (cudaStream_t)stream, 0.f,
+                     (flags & MCL_SHARDED_NORMALIZE_Q) ? MCL_SCAN_NORMALIZE_Q : 0);
   if (rc) return rc;
   NcclApi* n = nullptr;
   if (world > 1) {
@@ -700,6 +729,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 13) return g_opt_noseed.exchange(value);
   if (opt == 14) return g_opt_notop1.exchange(value);
   if (opt == 15) return g_opt_filter.exchange(value);
+  if (opt == 16) return g_opt_noqnorm.exchange(value);
   if (opt == 103) return drift_timeouts_total();
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;

@@ -31,6 +31,10 @@ struct ScanArgs {
   int tile_stride;           // seed mode: plan tile t = table tile t * tile_stride
   void* seed_max;            // seed mode: [sample chunks][seed_ld] uint32 keys of the chunk maxima
   int64_t seed_ld;
+  int qnorm_in_kernel;       // tcgen05 scan computes 1/||q_row|| itself (small batches) -> inv_q_out
+  float* inv_q_out;
+  void* clear_words;         // uint32 words the scan's CTA 0 zeroes for the next kernel (nullable)
+  int n_clear;
 };
 
 // Tile plan of the tcgen05 scan (plan.h).  ctas / gu / cluster = 0: heuristic.  leftover = 0
@@ -49,6 +53,7 @@ struct Workspace {
   void* joint;        // joint-threshold words (follow sync_ctr)
   size_t zero_bytes;  // tau_shared + sync_ctr + joint: cleared before every scan
   SlotView sv;
+  float* inv_q;       // [padded rows] scratch: query inverse norms the library computed itself
   void* extra;        // path-specific tail (small-batch path: score dump + per-range lists)
   int nslots;
   size_t bytes;

@@ -283,6 +283,8 @@ cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q
                          cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(merge_slots_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(merge_slots_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(merge_ranks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     pref_set[dev].store(true);
@@ -290,6 +292,13 @@ cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q
   // few rows with many slots (small Q split over all SMs): more warps per row
   if (map.stride > 32 && Q <= 4096)
     merge_slots_kernel<16><<<(unsigned)Q, 32 * 16, 0, s>>>(
+        sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
+        (float4*)row_stats);
+  // A warp walks its slots one after the other (count -> entries -> sort: a dependent chain of L2
+  // round trips per slot), so rows with 8+ slots are split over four warps while the launch still
+  // fits the chip in a wave or two
+  else if (map.stride >= 8 && Q <= 16384)
+    merge_slots_kernel<4><<<(unsigned)Q, 128, 0, s>>>(
         sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
   else

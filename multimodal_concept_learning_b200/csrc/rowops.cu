@@ -2,104 +2,20 @@
 // gather-mean(-normalise).  One warp per row, 128-bit coalesced loads, fp32 arithmetic.
 // Algorithmic bytes: inv-norm reads rows*dim*elt and writes rows*4; gather-mean reads
 // nnz*D*elt (+ the CSR arrays) and writes Q*D*elt.
-#include <float.h>
 #include "kernels.h"
+#include "rownorm.cuh"
 
 namespace mcl {
-
-constexpr float kTinyNorm = 10.0f * FLT_EPSILON;  // sklearn: norms below this become 1
-
-template <typename T> struct Vec;  // 16-byte vector of T
-template <> struct Vec<__nv_bfloat16> {
-  static constexpr int N = 8;
-  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 v = __bfloat1622float2(h[i]);
-      f[2 * i] = v.x; f[2 * i + 1] = v.y;
-    }
-  }
-  __device__ static __forceinline__ void widen(const uint4& u, float (&f)[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 v = __bfloat1622float2(h[i]);
-      f[2 * i] = v.x; f[2 * i + 1] = v.y;
-    }
-  }
-  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = u;
-  }
-  __device__ static __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-  __device__ static __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-};
-template <> struct Vec<float> {
-  static constexpr int N = 4;
-  __device__ static __forceinline__ void load(const float* p, float (&f)[4]) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-  }
-  __device__ static __forceinline__ void widen(const uint4& u, float (&f)[4]) {
-    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
-  }
-  __device__ static __forceinline__ void store(float* p, const float (&f)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
-  }
-  __device__ static __forceinline__ float ld1(const float* p) { return *p; }
-  __device__ static __forceinline__ void st1(float* p, float v) { *p = v; }
-};
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 row_inv_norm_kernel(const T* __restrict__ x, long long rows, int dim, long long ld,
                     float* __restrict__ out) {
-  constexpr int N = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const T* p = x + row * ld;
-  const int nvec = dim / N;
-  float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
-  int v = lane;
-  for (; v + 96 < nvec; v += 128) {  // four independent 16-byte loads in flight per lane
-    float a[N], b[N], c[N], d[N];
-    Vec<T>::load(p + (size_t)v * N, a);
-    Vec<T>::load(p + (size_t)(v + 32) * N, b);
-    Vec<T>::load(p + (size_t)(v + 64) * N, c);
-    Vec<T>::load(p + (size_t)(v + 96) * N, d);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      ss0 = fmaf(a[i], a[i], ss0); ss1 = fmaf(b[i], b[i], ss1);
-      ss2 = fmaf(c[i], c[i], ss2); ss3 = fmaf(d[i], d[i], ss3);
-    }
-  }
-  for (; v < nvec; v += 32) {
-    float a[N];
-    Vec<T>::load(p + (size_t)v * N, a);
-#pragma unroll
-    for (int i = 0; i < N; ++i) ss0 = fmaf(a[i], a[i], ss0);
-  }
-  for (int e = nvec * N + lane; e < dim; e += 32) {
-    const float a = Vec<T>::ld1(p + e);
-    ss1 = fmaf(a, a, ss1);
-  }
-  const float ss = warp_sum((ss0 + ss1) + (ss2 + ss3));
-  if (lane == 0) {
-    const float n = sqrtf(ss);
-    out[row] = (n < kTinyNorm) ? 1.0f : 1.0f / n;
-  }
+  const float inv = warp_row_inv_norm<T>(x + row * ld, dim, lane);
+  if (lane == 0) out[row] = inv;
 }
 
 // out[i,:] = mean of the gathered rows (fp32 sum in id order, true division, one rounding);

@@ -189,6 +189,7 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t e
   const size_t o_cand = take((size_t)nslots * kBlockM * kCandCap * sizeof(uint2));
   const size_t o_cnt = take((size_t)nslots * kBlockM * sizeof(int2));
   const size_t o_stats = take((size_t)nslots * kBlockM * sizeof(float4));
+  const size_t o_qn = take((size_t)num_rb * kBlockM * sizeof(float));
   const size_t o_extra = take(extra_bytes);
   w.bytes = off;
   w.zero_bytes = o_joint + (((size_t)num_rb * kBlockM * kJointWords * sizeof(uint32_t) + 255) & ~(size_t)255) - o_tau;
@@ -201,6 +202,7 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t e
     w.sv.cand = (uint2*)(b + o_cand);
     w.sv.cnt = (int2*)(b + o_cnt);
     w.sv.stats = (float4*)(b + o_stats);
+    w.inv_q = (float*)(b + o_qn);
     w.extra = (void*)(b + o_extra);
   }
   return w;
@@ -311,6 +313,10 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
   p.tile_stride = a.tile_stride > 0 ? a.tile_stride : 1;
   p.seed_max = (uint32_t*)a.seed_max; p.seed_ld = (int)a.seed_ld;
   p.drift_timeouts = drift_word(dev);
+  p.q_rows = a.qnorm_in_kernel ? (const __nv_bfloat16*)a.q : nullptr;
+  p.ldq = a.ldq;
+  p.inv_q_out = a.inv_q_out;
+  p.clear_words = (uint32_t*)a.clear_words; p.n_clear = a.n_clear;
   p.pol_q = (a.l2_mode & 1) ? kL2EvictLast : kL2EvictNormal;
   p.pol_t = (a.l2_mode & 2) ? kL2EvictFirst : ((a.l2_mode & 4) ? kL2EvictLast : kL2EvictNormal);
   const bool cap = a.softcap > 0.f;

@@ -27,6 +27,7 @@
 #pragma once
 #include <cuda.h>
 #include "rowstate.cuh"
+#include "rownorm.cuh"
 #include "kernels.h"
 
 namespace mcl {
@@ -64,6 +65,13 @@ struct TcParams {
   uint32_t* seed_max;           // seed mode: [chunks of the sample][seed_ld] keys of the chunk maxima
   int seed_ld;                  // padded query rows
   unsigned long long* drift_timeouts;   // mapped host word: drift waits that gave up (nullable)
+  // small query batches (one row block, Q <= 64): the kernel computes 1/||q_row|| itself instead of
+  // reading inv_q (one launch less where launches bound the step) and CTA 0 publishes the values
+  const __nv_bfloat16* q_rows;  // nullable: off
+  long long ldq;
+  float* inv_q_out;             // [padded rows] (CTA 0 writes; the merge reads)
+  uint32_t* clear_words;        // words CTA 0 zeroes for the kernel that FOLLOWS this one (nullable)
+  int n_clear;
 };
 
 // Epilogue modes (one template instantiation each):
@@ -114,6 +122,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_t);
   }
+  if (p.clear_words && blockIdx.x == 0)     // e.g. the selection kernel's per-row arrival counters
+    for (int i = threadIdx.x; i < p.n_clear; i += kTcThreads) p.clear_words[i] = 0u;
   if (warp == 1) {
     if (lane == 0) {
       // full: the (leader's) producer arms it; empty / tfull: one tcgen05.commit arrival;
@@ -258,7 +268,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       warp_buf = slot_buf + (size_t)(quarter * 32) * kCandCap;
       row = (long long)rb * kBlockM + row_in_tile;
       if (kMode == kModeTopK && (row >= p.Q || p.small_scores)) st.tau = INFINITY;   // padding rows (and the small-batch path) never append
-      rs = ((row < p.Q && p.inv_q) ? p.inv_q[row] : 1.f) * p.scale;
+      float invq = 1.f;
+      if (p.q_rows) {
+        // the warp's 32 rows one after the other, 32 lanes per row (rownorm.cuh: the same function,
+        // hence the same bits, as row_inv_norm_kernel); hidden behind the first tile's loads
+        const long long r0 = (long long)rb * kBlockM + quarter * 32;
+        for (int i = 0; i < 32 && r0 + i < p.Q; ++i) {
+          const float v = warp_row_inv_norm<__nv_bfloat16>(p.q_rows + (r0 + i) * p.ldq, p.D, lane);
+          if (lane == i) invq = v;
+        }
+        if (blockIdx.x == 0 && half == 0 && row < p.Q) p.inv_q_out[row] = invq;
+      } else if (row < p.Q && p.inv_q) {
+        invq = p.inv_q[row];
+      }
+      rs = invq * p.scale;
       a = (kCap ? p.softcap : rs) * kLog2e;
       const float rc = kCap ? rs / p.softcap : 0.f;
       lab_local = -1;

@@ -127,7 +127,8 @@ def _(stats, labels, label_smoothing, vocab):
 @torch.library.custom_op("mcl::concept_scan", mutates_args=(), device_types="cuda")
 def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
                      inv_norm_t: Optional[Tensor], labels: Optional[Tensor], scale: float,
-                     k: int, index_base: int, softcap: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
+                     k: int, index_base: int, softcap: float = 0.0,
+                     normalize_q: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     lib = load()
     dev = q.device
     Q, D = q.shape
@@ -139,24 +140,19 @@ def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
     with torch.cuda.device(dev):
         ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        if softcap > 0.0:
-            check(lib.mcl_concept_scan_softcap(q.data_ptr(), table.data_ptr(), code, Q, V, D,
-                                               q.stride(0), table.stride(0), _ptr(inv_norm_q),
-                                               _ptr(inv_norm_t), float(scale), float(softcap), k,
-                                               index_base, _ptr(labels), val.data_ptr(),
-                                               idx.data_ptr(), stats.data_ptr(), ws.data_ptr(),
-                                               ws_bytes, None, _stream(dev)))
-        else:
-            check(lib.mcl_concept_scan(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
-                                       table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t),
-                                       float(scale), k, index_base, _ptr(labels), val.data_ptr(),
-                                       idx.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes,
-                                       _stream(dev)))
+        # normalize_q without caller-supplied norms: the library forms them (inside the scan kernel
+        # for small batches -- MCL_SCAN_NORMALIZE_Q)
+        flags = 1 if (normalize_q and inv_norm_q is None) else 0
+        check(lib.mcl_concept_scan_ex(q.data_ptr(), table.data_ptr(), code, Q, V, D, q.stride(0),
+                                      table.stride(0), _ptr(inv_norm_q), _ptr(inv_norm_t), float(scale),
+                                      float(softcap), k, index_base, _ptr(labels), val.data_ptr(),
+                                      idx.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, flags,
+                                      _stream(dev)))
     return val, idx, stats
 
 
 @_concept_scan_op.register_fake
-def _(q, table, inv_norm_q, inv_norm_t, labels, scale, k, index_base, softcap=0.0):
+def _(q, table, inv_norm_q, inv_norm_t, labels, scale, k, index_base, softcap=0.0, normalize_q=False):
     Q = q.shape[0]
     return (q.new_empty((Q, k), dtype=torch.float32), q.new_empty((Q, k), dtype=torch.int64),
             q.new_empty((Q, 4), dtype=torch.float32))
@@ -273,8 +269,6 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
     if not scale > 0:
         raise ValueError("scale must be > 0")
     q, table = _rowmajor(q), _rowmajor(table)
-    if normalize_q and inv_norm_q is None:
-        inv_norm_q = torch.ops.mcl.row_inv_norm(q)
     if normalize_t and inv_norm_t is None:
         inv_norm_t = torch.ops.mcl.row_inv_norm(table)
     if inv_norm_q is not None:
@@ -297,7 +291,7 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
         raise ValueError("softcap must be > 0 (or None)")
     val, idx, stats = torch.ops.mcl.concept_scan(q, table, inv_norm_q, inv_norm_t, labels,
                                                  float(scale), int(k), int(index_base),
-                                                 float(softcap or 0.0))
+                                                 float(softcap or 0.0), bool(normalize_q))
     return ScanOutput(val, idx, stats, int(vocab_total or table.shape[0]), labels,
                       float(label_smoothing))
 

@@ -138,8 +138,7 @@ class ShardedConceptScan:
                              f"{ops.MCL_MAX_K})]")
         q = ops._rowmajor(q)
         Q, D = q.shape
-        if normalize_q and inv_norm_q is None:
-            inv_norm_q = ops.row_inv_norm(q)
+        flags = (1 if local_rows_only else 0) | (2 if (normalize_q and inv_norm_q is None) else 0)
         if labels is not None:
             labels = labels.to(device=dev, dtype=torch.int64).contiguous()
         code = ops._dtype_code(q)
@@ -157,7 +156,7 @@ class ShardedConceptScan:
                 self.table.stride(0), ops._ptr(inv_norm_q), ops._ptr(self.inv_norm_t), float(scale),
                 kk, self.lo, ops._ptr(labels), val.data_ptr(), idx.data_ptr(), stats.data_ptr(),
                 ws.data_ptr(), ws_bytes, self._gather.data_ptr(), gbytes, self._comm, self.world,
-                self.rank, 1 if local_rows_only else 0, ops._stream(dev)))
+                self.rank, flags, ops._stream(dev)))
         return ops.ScanOutput(val, idx, stats, self.vocab_total, labels, float(label_smoothing))
 
 

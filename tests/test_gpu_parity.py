@@ -513,7 +513,7 @@ def test_top1_gemma3_vocab_shape(mcl):
     torch.testing.assert_close(out.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4)
     has = labels[sub] != -100
     torch.testing.assert_close(out.stats[sub, 3][has], z[has, labels[sub][has]], rtol=RTOL, atol=1e-4)
-    sel = torch.cat([torch.arange(0, 8, device="cuda"), lab_rows])
+    sel = (labels != -100).nonzero().flatten()
     zl = q[sel].float() @ t.float().T
     want = torch.nn.functional.cross_entropy(zl, labels[sel])
     torch.testing.assert_close(out.loss, want, rtol=RTOL, atol=1e-5)
@@ -539,7 +539,9 @@ def test_threshold_seeding_changes_nothing(mcl, Q, V, D, k, scale):
     finally:
         mcl.set_option(13, old)
     assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
-    assert torch.equal(a.stats, b.stats)
+    # (the seeded scan plans with a cheaper restart charge: another partition of the columns,
+    # another summation order of the statistics)
+    torch.testing.assert_close(a.stats, b.stats, rtol=1e-5, atol=1e-5 * scale)
     if Q * V <= 20_000_000:
         ref = R.concept_scan_ref(q, t, k, scale=scale, labels=labels, keep_scores=True)
         check_topk(a.topk_val, a.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-5 * scale)
