@@ -415,8 +415,11 @@ def run_workload(name, steps, warmup, world, rank, device, with_e2e=True, sample
         # HostQueryPipeline overlaps the copies of neighbouring steps with the scan.
         from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
         q_host = q.cpu().pin_memory()
+        # (N > 1: every rank uploads 1/N of the batch, pushes it to the peers over NVLink with copy
+        # engines and takes home the 1/N of the result rows it merged)
         pipe = HostQueryPipeline(table, w["k"], normalize=w["normalize"], scale=w["scale"],
-                                 inv_norm_t=step.inv_t, scanner=step.scanner, reuse_host_buffers=True)
+                                 inv_norm_t=step.inv_t, scanner=step.scanner, reuse_host_buffers=True,
+                                 local_rows=world > 1)
         outs = None
         # (warm-up long enough for the pinned result buffers of all batches in flight to come from
         # torch's host-allocator cache: a cudaHostAlloc inside the timed region costs milliseconds)
@@ -433,9 +436,30 @@ def run_workload(name, steps, warmup, world, rank, device, with_e2e=True, sample
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         res["e2e"] = {"value": w["Q"] * steps / float(dt), "unit": "queries/s",
+                      "ms_per_step": 1e3 * float(dt) / steps,
                       "h2d_bytes_per_step": pipe.h2d_bytes_per_step(q_host),
-                      "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in outs),
+                      # summed over the ranks (each copies the rows it merged; all rows at N <= 2)
+                      "d2h_bytes_per_step": world * sum(t.numel() * t.element_size() for t in outs),
                       "note": pipe.describe()}
+        if world > 1 and pipe._board is not None:
+            # where a step's time goes: the query distribution alone (upload of 1/N + pushes to the
+            # peers + the wait for every peer's slice), device-timed, without any scan behind it
+            board, cs = pipe._board, pipe.copy_stream
+            main = torch.cuda.current_stream(device)
+            for _ in range(3):
+                board.wait(*board.publish(q_host, cs), main)
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            for _ in range(steps):
+                board.wait(*board.publish(q_host, cs), main)
+            e1.record(main)
+            torch.cuda.synchronize(device)
+            dms = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+            res["e2e"]["breakdown_ms"] = {"scan_exchange_merge": ms / steps, "distribute_queries_alone": float(dms),
+                                          "e2e_step": 1e3 * float(dt) / steps}
         pipe.close()
     if check:
         res["parity_check"] = parity_check(w, step, q, table, labels, lo, hi, world, rank, device)

@@ -96,4 +96,57 @@ __device__ __forceinline__ float warp_row_inv_norm(const T* __restrict__ p, int 
   return (n < kTinyNorm) ? 1.0f : 1.0f / n;
 }
 
+// R rows at once (p, p + stride, ...): the loads of all R rows are issued before any is reduced, so
+// a warp that needs the norms of several rows pays one memory round trip per R rows.  Per row the
+// arithmetic and its order are those of warp_row_inv_norm: the results are bit-identical.
+template <typename T, int R>
+__device__ __forceinline__ void warp_rows_inv_norm(const T* __restrict__ p, long long stride, int nrows,
+                                                   int dim, int lane, float (&out)[R]) {
+  constexpr int N = Vec<T>::N;
+  const int nvec = dim / N;
+  float ss0[R], ss1[R], ss2[R], ss3[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { ss0[r] = 0.f; ss1[r] = 0.f; ss2[r] = 0.f; ss3[r] = 0.f; }
+  int v = lane;
+  for (; v + 96 < nvec; v += 128) {
+    float a[R][N], b[R][N], c[R][N], d[R][N];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const T* q = p + (r < nrows ? r : 0) * stride;
+      Vec<T>::load(q + (size_t)v * N, a[r]);
+      Vec<T>::load(q + (size_t)(v + 32) * N, b[r]);
+      Vec<T>::load(q + (size_t)(v + 64) * N, c[r]);
+      Vec<T>::load(q + (size_t)(v + 96) * N, d[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        ss0[r] = fmaf(a[r][i], a[r][i], ss0[r]); ss1[r] = fmaf(b[r][i], b[r][i], ss1[r]);
+        ss2[r] = fmaf(c[r][i], c[r][i], ss2[r]); ss3[r] = fmaf(d[r][i], d[r][i], ss3[r]);
+      }
+  }
+  for (; v < nvec; v += 32) {
+    float a[R][N];
+#pragma unroll
+    for (int r = 0; r < R; ++r) Vec<T>::load(p + (r < nrows ? r : 0) * stride + (size_t)v * N, a[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < N; ++i) ss0[r] = fmaf(a[r][i], a[r][i], ss0[r]);
+  }
+  for (int e = nvec * N + lane; e < dim; e += 32) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float a = Vec<T>::ld1(p + (r < nrows ? r : 0) * stride + e);
+      ss1[r] = fmaf(a, a, ss1[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float n = sqrtf(warp_sum((ss0[r] + ss1[r]) + (ss2[r] + ss3[r])));
+    out[r] = (n < kTinyNorm) ? 1.0f : 1.0f / n;
+  }
+}
+
 }  // namespace mcl

@@ -273,9 +273,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // the warp's 32 rows one after the other, 32 lanes per row (rownorm.cuh: the same function,
         // hence the same bits, as row_inv_norm_kernel); hidden behind the first tile's loads
         const long long r0 = (long long)rb * kBlockM + quarter * 32;
-        for (int i = 0; i < 32 && r0 + i < p.Q; ++i) {
-          const float v = warp_row_inv_norm<__nv_bfloat16>(p.q_rows + (r0 + i) * p.ldq, p.D, lane);
-          if (lane == i) invq = v;
+        for (int i = 0; i < 32 && r0 + i < p.Q; i += 4) {      // four rows per memory round trip
+          float v[4];
+          const int nr = (int)(p.Q - (r0 + i) < 4 ? p.Q - (r0 + i) : 4);
+          warp_rows_inv_norm<__nv_bfloat16, 4>(p.q_rows + (r0 + i) * p.ldq, p.ldq, nr, p.D, lane, v);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (lane == i + r) invq = v[r];
         }
         if (blockIdx.x == 0 && half == 0 && row < p.Q) p.inv_q_out[row] = invq;
       } else if (row < p.Q && p.inv_q) {
