@@ -193,6 +193,38 @@ int mcl_ce_from_stats(const float* row_stats /*[Q,4]*/, const int64_t* labels /*
                       float* loss_mean /*[2]*/, mcl_stream_t stream);
 
 /*
+ * Backward of the fused cross-entropy: with loss = mean over the n rows
+ * (all of which carry a label; the caller passes only those) of CE(scale * q T^T, labels) as the
+ * forward scan computed it, and lse[i] the log-sum-exp that scan returned,
+ *     dL/dz[i,j]  = (exp(z_ij - lse_i) - (1-eps) [j = label_i] - eps / vocab_total) * *grad_loss / n_valid
+ *     grad_q      = scale * dL/dz  * T      [n, D]  fp32, pitch D
+ *     grad_table  = scale * dL/dz^T * q     [V, D]  fp32, pitch D
+ * (softcap > 0: z' = softcap * tanh(z / softcap) and the factor 1 - tanh^2 rides along.)  Either
+ * gradient pointer may be NULL.  bf16 inputs: the scores are recomputed tile by tile by the tcgen05
+ * scan kernel, whose grad epilogue writes dL/dz in bf16 for a block of <= 4096 rows x a chunk of
+ * table rows (<= 64 MB, L2-resident) into the workspace, and two tcgen05 GEMMs (csrc/gemm_tc.cu,
+ * MN-major operand descriptors: no transposed copy of anything) consume it; the [n x V] matrix is
+ * never materialised.  fp32 inputs: CUDA-core check path (rtol 1e-4).
+ * Replaces: `accelerator.backward(loss)` through lm_head + ForCausalLMLoss,
+ *   src/multimodal/multimodal_training.py:140 (`language_embed_only` trains the table itself,
+ *   src/multimodal/mllm.py:181-184), and through the classifier head, src/vision/vision_training.py:120.
+ */
+size_t mcl_ce_backward_workspace_bytes(int64_t n, int64_t V, int64_t D, int dtype);
+int mcl_ce_backward(const void* q /*[n,D]*/, const void* table /*[V,D]*/, int dtype, int64_t n, int64_t V,
+                    int64_t D, int64_t ldq, int64_t ldt, const float* lse /*[n]*/,
+                    const int64_t* labels /*[n]*/, float scale, float softcap, float label_smoothing,
+                    int64_t vocab_total, const float* grad_loss /*device scalar*/, int64_t n_valid,
+                    float* grad_q /*[n,D] nullable*/, float* grad_table /*[V,D] nullable*/,
+                    void* workspace, size_t workspace_bytes, mcl_stream_t stream);
+
+/*
+ * The GEMM of that backward on its own: C[M,N] fp32 (+)= A * B, bf16 operands on tcgen05.
+ * a_mn = 0: A is stored [M][K] (pitch lda); a_mn = 1: A is stored [K][M].  Same for B with N.
+ */
+int mcl_gemm_bf16(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb, float* c,
+                  int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, mcl_stream_t stream);
+
+/*
  * Vocabulary-sharded scan over the GPUs of one NVSwitch box: local scan, ONE ncclAllGather
  * of the packed per-rank record, local merge -- all enqueued on `stream`.
  * The library owns only the communicator.  `unique_id` is the 128-byte ncclUniqueId (host),

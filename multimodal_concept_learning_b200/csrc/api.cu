@@ -482,6 +482,138 @@ int mcl_ce_from_stats(const float* row_stats, const int64_t* labels, int64_t Q, 
   return MCL_OK;
 }
 
+// ---- backward of the fused cross-entropy ------------------------------------------------------
+namespace {
+struct BwdBlocking { int64_t nb, vc, p_bytes; };
+constexpr size_t kBwdPBytes = 64u << 20;          // dL/dz block: written once, read twice, mostly out of L2
+BwdBlocking bwd_blocking(int64_t n, int64_t V, int dtype) {
+  BwdBlocking b{};
+  if (dtype == MCL_DTYPE_BF16) {
+    const int64_t n_pad = (n + kBlockM - 1) / kBlockM * kBlockM;
+    b.nb = n_pad < 4096 ? n_pad : 4096;
+    int64_t vc = (int64_t)(kBwdPBytes / (size_t)(b.nb * 2)) / kBlockN * kBlockN;
+    const int64_t v_pad = (V + kBlockN - 1) / kBlockN * kBlockN;
+    b.vc = vc < kBlockN ? kBlockN : (vc > v_pad ? v_pad : vc);
+    b.p_bytes = b.nb * b.vc * 2;
+  } else {
+    b.nb = n;
+    int64_t vc = (int64_t)(kBwdPBytes / (size_t)((n > 0 ? n : 1) * 4)) / 64 * 64;
+    const int64_t v_pad = (V + 63) / 64 * 64;
+    b.vc = vc < 64 ? 64 : (vc > v_pad ? v_pad : vc);
+    b.p_bytes = b.nb * b.vc * 4;
+  }
+  return b;
+}
+}  // namespace
+
+size_t mcl_ce_backward_workspace_bytes(int64_t n, int64_t V, int64_t D, int dtype) {
+  (void)D;
+  if (n <= 0 || V <= 0) return 256;
+  return (size_t)((bwd_blocking(n, V, dtype).p_bytes + 255) & ~(int64_t)255);
+}
+
+int mcl_ce_backward(const void* q, const void* table, int dtype, int64_t n, int64_t V, int64_t D, int64_t ldq,
+                    int64_t ldt, const float* lse, const int64_t* labels, float scale, float softcap,
+                    float label_smoothing, int64_t vocab_total, const float* grad_loss, int64_t n_valid,
+                    float* grad_q, float* grad_table, void* workspace, size_t workspace_bytes,
+                    mcl_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (dtype != MCL_DTYPE_BF16 && dtype != MCL_DTYPE_F32) return fail(MCL_ERR_BAD_ARG, "dtype %d", dtype);
+  if (n < 0 || V < 1 || D < 1 || ldq < D || ldt < D || vocab_total < 1 || n_valid < 1)
+    return fail(MCL_ERR_BAD_ARG, "bad shape n=%lld V=%lld D=%lld", (long long)n, (long long)V, (long long)D);
+  if (n >= (1ll << 31) || V >= (1ll << 31)) return fail(MCL_ERR_BAD_ARG, "shape exceeds 2^31");
+  if (!(scale > 0.f) || !(softcap >= 0.f) || !(label_smoothing >= 0.f) || !(label_smoothing <= 1.f))
+    return fail(MCL_ERR_BAD_ARG, "bad scale / softcap / label_smoothing");
+  if (n > 0 && (!q || !lse || !labels || !grad_loss)) return fail(MCL_ERR_BAD_ARG, "null pointer");
+  if (!table) return fail(MCL_ERR_BAD_ARG, "null table");
+  const size_t es = elt_size(dtype);
+  if (!aligned16(q) || !aligned16(table) || (ldq * es) % 16 || (ldt * es) % 16 || !aligned16(grad_q) ||
+      !aligned16(grad_table) || (D % 4))
+    return fail(MCL_ERR_UNALIGNED, "q / table / gradient rows must be 16-byte aligned");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  if (n == 0 || (!grad_q && !grad_table)) return MCL_OK;
+  const BwdBlocking bl = bwd_blocking(n, V, dtype);
+  if (!workspace || workspace_bytes < (size_t)bl.p_bytes || !aligned16(workspace))
+    return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "workspace %zu B < required %lld B", workspace_bytes, (long long)bl.p_bytes);
+  const float eps_over_v = label_smoothing / (float)vocab_total, one_minus_eps = 1.f - label_smoothing;
+  const float coef = 1.f / (float)n_valid;
+  cudaError_t e;
+  if (dtype == MCL_DTYPE_F32) {
+    // check path: Z = q Tc^T -> dL/dz in place -> the two gradient products, chunk by chunk over the table
+    float* P = (float*)workspace;
+    const float* qf = (const float*)q;
+    const float* tf = (const float*)table;
+    for (int64_t v0 = 0; v0 < V; v0 += bl.vc) {
+      const int64_t vc = V - v0 < bl.vc ? V - v0 : bl.vc;
+      e = launch_gemm_simt(qf, ldq, 1, tf + v0 * ldt, 1, ldt, P, bl.vc, n, vc, D, 0, stream);
+      if (e == cudaSuccess)
+        e = launch_dz_simt(P, bl.vc, n, vc, v0, lse, labels, scale, softcap, eps_over_v, one_minus_eps, grad_loss,
+                           coef * scale, stream);
+      if (e == cudaSuccess && grad_q)
+        e = launch_gemm_simt(P, bl.vc, 1, tf + v0 * ldt, ldt, 1, grad_q, D, n, D, vc, v0 > 0, stream);
+      if (e == cudaSuccess && grad_table)
+        e = launch_gemm_simt(P, 1, bl.vc, qf, ldq, 1, grad_table + v0 * D, D, vc, D, n, 0, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "backward (fp32 check path) launch");
+      g_launches += 2 + (grad_q ? 1 : 0) + (grad_table ? 1 : 0);
+    }
+    return MCL_OK;
+  }
+  // tcgen05 path: for every block of rows, walk the table in chunks: dL/dz block (scan kernel, grad
+  // epilogue) -> dL/dq += P T (accumulates over the chunks) and dL/dT chunk (+)= P^T q (accumulates
+  // over the row blocks)
+  const __nv_bfloat16* qb = (const __nv_bfloat16*)q;
+  const __nv_bfloat16* tb = (const __nv_bfloat16*)table;
+  PlanKnobs kn = knobs();
+  kn.filter = 2;
+  char msg[256] = "";
+  for (int64_t r0 = 0; r0 < n; r0 += bl.nb) {
+    const int64_t rows = n - r0 < bl.nb ? n - r0 : bl.nb;
+    for (int64_t v0 = 0; v0 < V; v0 += bl.vc) {
+      const int64_t vc = V - v0 < bl.vc ? V - v0 : bl.vc;
+      const TcPlan plan = make_tc_plan(rows, vc, D, di.sm, kn);
+      ScanArgs a{};
+      a.q = qb + r0 * ldq; a.table = tb + v0 * ldt; a.dtype = dtype; a.Q = rows; a.V = vc; a.D = D;
+      a.ldq = ldq; a.ldt = ldt; a.scale = scale; a.k = 1; a.index_base = v0; a.labels = labels + r0;
+      a.softcap = softcap; a.mode = 3; a.tile_stride = 1;
+      a.p_out = workspace; a.ldp = bl.vc; a.p_rows = bl.nb;
+      a.lse = lse + r0; a.grad_loss = grad_loss; a.grad_coef = coef * scale;
+      a.eps_over_v = eps_over_v; a.one_minus_eps = one_minus_eps;
+      e = launch_scan_tc(a, plan, SlotView{}, stream, msg, sizeof(msg));
+      if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "backward dL/dz launch: %s %s", cudaGetErrorString(e), msg);
+      g_launches++;
+      if (grad_q) {
+        e = launch_gemm_tc(workspace, 0, bl.vc, tb + v0 * ldt, 1, ldt, grad_q + r0 * D, D, rows, D, vc, v0 > 0,
+                           di.sm, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "backward dL/dq GEMM launch");
+        g_launches++;
+      }
+      if (grad_table) {
+        e = launch_gemm_tc(workspace, 1, bl.vc, qb + r0 * ldq, 1, ldq, grad_table + v0 * D, D, vc, D, rows, r0 > 0,
+                           di.sm, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "backward dL/dT GEMM launch");
+        g_launches++;
+      }
+    }
+  }
+  return MCL_OK;
+}
+
+int mcl_gemm_bf16(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb, float* c,
+                  int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, mcl_stream_t stream) {
+  if (M < 0 || N < 0 || K < 1 || !a || !b || !c) return fail(MCL_ERR_BAD_ARG, "bad GEMM arguments");
+  if (!aligned16(a) || !aligned16(b) || !aligned16(c) || (lda * 2) % 16 || (ldb * 2) % 16)
+    return fail(MCL_ERR_UNALIGNED, "operand bases and pitches must be multiples of 16 bytes");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  cudaError_t e = launch_gemm_tc(a, a_mn, lda, b, b_mn, ldb, c, ldc, M, N, K, accumulate, di.sm, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "gemm launch");
+  g_launches++;
+  return MCL_OK;
+}
+
 int mcl_comm_unique_id(void* unique_id_out) {
   NcclApi* n = nccl();
   if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror() ? dlerror() : "");

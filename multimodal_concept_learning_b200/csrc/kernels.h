@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "plan.h"
 
+struct CUtensorMap_st;   // <cuda.h>: CUtensorMap
+
 namespace mcl {
 
 struct ScanArgs {
@@ -35,6 +37,9 @@ struct ScanArgs {
   float* inv_q_out;
   void* clear_words;         // uint32 words the scan's CTA 0 zeroes for the next kernel (nullable)
   int n_clear;
+  // grad mode (mode 3): dL/dz tiles for the backward GEMMs
+  void* p_out; int64_t ldp; int64_t p_rows;
+  const float* lse; const float* grad_loss; float grad_coef, eps_over_v, one_minus_eps;
 };
 
 // Tile plan of the tcgen05 scan (plan.h).  ctas / gu / cluster = 0: heuristic.  leftover = 0
@@ -61,6 +66,18 @@ struct Workspace {
 // carve `nslots` slots out of a caller buffer (base may be null to only size it)
 Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t extra_bytes);
 
+// 2-D bf16 row-major [rows, cols] (pitch ld elements) -> TMA tiles of box_rows x 64, SWIZZLE_128B
+bool make_tmap_bf16(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+// C[M,N] fp32 (+)= A * B on tcgen05 (gemm_tc.cu); *_mn = 1: the operand is stored [K][M or N]
+cudaError_t launch_gemm_tc(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb,
+                           float* c, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate,
+                           int sm_count, cudaStream_t s);
+// fp32 check path of the backward (bwd_simt.cu): C (+)= op(A) * op(B) with arbitrary strides, and Z -> dL/dz in place
+cudaError_t launch_gemm_simt(const float* a, int64_t sa_m, int64_t sa_k, const float* b, int64_t sb_k, int64_t sb_n,
+                             float* c, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t s);
+cudaError_t launch_dz_simt(float* z, int64_t ldz, int64_t rows, int64_t cols, int64_t col_base, const float* lse,
+                           const int64_t* labels, float scale, float softcap, float eps_over_v, float one_minus_eps,
+                           const float* grad_loss, float grad_coef, cudaStream_t s);
 cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView& sv,
                            cudaStream_t s, char* err, size_t errlen);
 long long drift_timeouts_total();   // drift waits of the tcgen05 scan that gave up (all devices)

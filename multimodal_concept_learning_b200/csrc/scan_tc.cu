@@ -228,8 +228,8 @@ static EncodeTiledFn get_encode_fn() {
 // 2-D bf16 row-major [rows, cols] (pitch ld elements) -> tiles of box_rows x 64, SWIZZLE_128B.
 // Descriptors depend only on (base, shape, pitch, box); the last few are cached per thread
 // because the same table (and query buffer) is scanned over and over.
-static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
-                      int box_rows) {
+bool make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows) {
   struct Entry { const void* base; int64_t rows, cols, ld; int box; CUtensorMap tm; bool ok; };
   thread_local Entry cache[8] = {};
   thread_local int next = 0;
@@ -288,13 +288,14 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
     cudaError_t e = tc_set_smem_attr_mode0();
     if (e == cudaSuccess) e = tc_set_smem_attr_mode1();
     if (e == cudaSuccess) e = tc_set_smem_attr_mode2();
+    if (e == cudaSuccess) e = tc_set_smem_attr_mode3();
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(smem=%u)", kTcSmemBytes); return e; }
     attr_set[dev].store(true);
   }
   const int cs = plan.cs;
   CUtensorMap tm_q, tm_t;
-  if (!make_tmap(&tm_q, a.q, a.Q, a.D, a.ldq, kBlockM) ||
-      !make_tmap(&tm_t, a.table, a.V, a.D, a.ldt, kBlockN / cs)) {
+  if (!make_tmap_bf16(&tm_q, a.q, a.Q, a.D, a.ldq, kBlockM) ||
+      !make_tmap_bf16(&tm_t, a.table, a.V, a.D, a.ldt, kBlockN / cs)) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (Q=%lld V=%lld D=%lld ldq=%lld ldt=%lld)",
              (long long)a.Q, (long long)a.V, (long long)a.D, (long long)a.ldq, (long long)a.ldt);
     return cudaErrorInvalidValue;
@@ -335,6 +336,10 @@ cudaError_t launch_scan_tc(const ScanArgs& a, const TcPlan& plan, const SlotView
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = cs == 2 ? attr : nullptr;
   cfg.numAttrs = cs == 2 ? 1 : 0;
+  p.p_out = (__nv_bfloat16*)a.p_out; p.ldp = a.ldp; p.p_rows = (int)a.p_rows;
+  p.lse = a.lse; p.grad_loss = a.grad_loss; p.grad_coef = a.grad_coef;
+  p.eps_over_v = a.eps_over_v; p.one_minus_eps = a.one_minus_eps;
+  if (a.mode == kModeGrad) return tc_launch_mode3(&cfg, cs, cap, tm_q, tm_t, p);
   if (a.mode == kModeSeed) return tc_launch_mode2(&cfg, cs, false, tm_q, tm_t, p);
   if (a.mode == kModeTop1) return tc_launch_mode1(&cfg, cs, cap, tm_q, tm_t, p);
   return tc_launch_mode0(&cfg, cs, cap, tm_q, tm_t, p);

@@ -72,6 +72,14 @@ struct TcParams {
   float* inv_q_out;             // [padded rows] (CTA 0 writes; the merge reads)
   uint32_t* clear_words;        // words CTA 0 zeroes for the kernel that FOLLOWS this one (nullable)
   int n_clear;
+  // grad mode (backward of the fused cross-entropy): dL/dz tiles, bf16, [p_rows][ldp]
+  __nv_bfloat16* p_out;
+  long long ldp;
+  int p_rows;
+  const float* lse;             // [Q] log-sum-exp saved by the forward (natural log)
+  const float* grad_loss;       // device scalar: dL/d(loss)
+  float grad_coef;              // 1 / rows with a label (the mean's denominator)
+  float eps_over_v, one_minus_eps;
 };
 
 // Epilogue modes (one template instantiation each):
@@ -84,7 +92,11 @@ struct TcParams {
 //              shared threshold words the main scan starts from).  Epilogue-bound shapes
 //              (D <= 1536) lose more time to the cold start of every slot's top-k filter
 //              (threshold -inf: every score is a candidate) than this sample costs.
-constexpr int kModeTopK = 0, kModeTop1 = 1, kModeSeed = 2;
+//   kModeGrad  backward of the fused cross-entropy: the scores are recomputed tile by tile and turned
+//              into dL/dz = (exp(z - lse) - (1-eps) [col = label] - eps/V) * dL/dloss / n_valid with the
+//              log-sum-exp the forward saved, rounded to bf16 and written as the operand of the two
+//              gradient GEMMs (gemm_tc.cu).  With a soft-cap the factor dz'/dz = 1 - tanh^2 rides along.
+constexpr int kModeTopK = 0, kModeTop1 = 1, kModeSeed = 2, kModeGrad = 3;
 
 // kCS = CTAs per cluster.  kCS = 1: every CTA multiplies its own 128 x 256 tile
 // (cta_group::1, 48 KB of operands per K slice, 4 stages).  kCS = 2: two consecutive members of
@@ -159,7 +171,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int rb = sg.unit * kCS + (int)crank;
         const int win = p.plan.win;
         // (a worker alone on its tiles has nobody to drift from; the seed pass is a few tiles long)
-        int* ctr = (kMode != kModeSeed && sg.sync >= 0 && sg.members > kCS) ? p.sync_ctr + sg.sync : nullptr;
+        int* ctr = (kMode != kModeSeed && kMode != kModeGrad && sg.sync >= 0 && sg.members > kCS) ? p.sync_ctr + sg.sync : nullptr;
         for (int vt = sg.vt0; vt < sg.vt1; ++vt) {
           // Drift bound: the members of a full group read the same table tiles and rely on L2
           // to fetch each from HBM once; nothing else keeps them together, and SMs differ in
@@ -286,6 +298,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         invq = p.inv_q[row];
       }
       rs = invq * p.scale;
+      float g_row = 0.f, lse2 = 0.f;                   // grad mode: dL/dloss / n_valid, lse * log2(e)
+      if (kMode == kModeGrad && row < p.Q && (!p.labels || p.labels[row] != -100)) {
+        g_row = __ldg(p.grad_loss) * p.grad_coef;
+        lse2 = p.lse[row] * kLog2e;
+      }
       a = (kCap ? p.softcap : rs) * kLog2e;
       const float rc = kCap ? rs / p.softcap : 0.f;
       lab_local = -1;
@@ -378,7 +395,35 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               dst[i] = make_float4(z[0], z[1], z[2], z[3]);
             }
           }
-          if (kMode == kModeSeed) {
+          if (kMode == kModeGrad) {
+            uint32_t packed[kChunk / 2];
+#pragma unroll
+            for (int i = 0; i < kChunk; i += 2) {
+              float v[2];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                float pr, d = 1.f;
+                if (kCap) {
+                  const float t = tanhf(y[i + j] * rc);
+                  pr = ex2_fast(fmaf(t, a, -lse2));      // a = softcap * log2(e)
+                  d = 1.f - t * t;
+                } else {
+                  pr = ex2_fast(fmaf(y[i + j], a, -lse2));
+                }
+                float x = pr - p.eps_over_v;
+                if (col0 + i + j == lab_local) x -= p.one_minus_eps;
+                v[j] = (i + j < n_valid) ? x * g_row * d : 0.f;
+              }
+              const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+              packed[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            if (row < (long long)p.p_rows) {
+              uint4* dst = reinterpret_cast<uint4*>(p.p_out + row * p.ldp + col0);
+#pragma unroll
+              for (int i = 0; i < kChunk / 8; ++i)
+                dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            }
+          } else if (kMode == kModeSeed) {
             // sample tiles are whole tiles: only the chunk maximum is kept (as a key, coalesced
             // over the warp's 32 rows)
             float m8[kChunk / 4];
@@ -418,7 +463,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tb ^= 1u;
       }
       if (kMode == kModeTop1) row_flush_top1(st);
-      if (kMode != kModeSeed)
+      if (kMode != kModeSeed && kMode != kModeGrad)
         row_flush(st, rs, kCap ? p.softcap : 0.f, p.sv.cnt + (size_t)slot * kBlockM + row_in_tile,
                   p.sv.stats + (size_t)slot * kBlockM + row_in_tile);
       sg = nx;
@@ -447,11 +492,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 cudaError_t tc_set_smem_attr_mode0();
 cudaError_t tc_set_smem_attr_mode1();
 cudaError_t tc_set_smem_attr_mode2();
+cudaError_t tc_set_smem_attr_mode3();
 cudaError_t tc_launch_mode0(const cudaLaunchConfig_t* cfg, int cs, bool cap, const CUtensorMap& tm_q,
                             const CUtensorMap& tm_t, const TcParams& p);
 cudaError_t tc_launch_mode1(const cudaLaunchConfig_t* cfg, int cs, bool cap, const CUtensorMap& tm_q,
                             const CUtensorMap& tm_t, const TcParams& p);
 cudaError_t tc_launch_mode2(const cudaLaunchConfig_t* cfg, int cs, bool cap, const CUtensorMap& tm_q,
+                            const CUtensorMap& tm_t, const TcParams& p);
+cudaError_t tc_launch_mode3(const cudaLaunchConfig_t* cfg, int cs, bool cap, const CUtensorMap& tm_q,
                             const CUtensorMap& tm_t, const TcParams& p);
 
 }  // namespace mcl

@@ -329,3 +329,76 @@ def test_a7_patched_vit_forward_and_criterion_reproduce_the_reference(eps):
     torch.testing.assert_close(model.classifier.bias.grad, ref.classifier.bias.grad, rtol=1e-3, atol=1e-5)
     gw, rw = model.vit.embeddings.cls_token.grad, ref.vit.embeddings.cls_token.grad
     torch.testing.assert_close(gw, rw, rtol=1e-2, atol=1e-5)
+
+
+# ---- round 2: native tcgen05 backward -------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 520, 200), (1000, 72, 1032), (77, 1152, 4104)])
+def test_gemm_bf16_all_operand_layouts(a_mn, b_mn, M, N, K):
+    """The backward's GEMM on its own: K-major and MN-major operand descriptors (the latter are what
+    make dL/dq = P T and dL/dT = P^T q transposition-free), ragged M / N / K, accumulate on / off."""
+    from multimodal_concept_learning_b200 import _lib, ops
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    pad = lambda x: -(-x // 8) * 8                                   # pitches: multiples of 16 bytes
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(K, N, generator=g).to(torch.bfloat16).cuda()
+    want = A.float() @ B.float()
+    a_store = torch.zeros((K, pad(M)) if a_mn else (M, pad(K)), dtype=torch.bfloat16, device="cuda")
+    b_store = torch.zeros((K, pad(N)) if b_mn else (N, pad(K)), dtype=torch.bfloat16, device="cuda")
+    (a_store[:, :M] if a_mn else a_store[:, :K]).copy_(A.t() if a_mn else A)
+    (b_store[:, :N] if b_mn else b_store[:, :K]).copy_(B if b_mn else B.t())
+    C = torch.full((M, N), 3.0, dtype=torch.float32, device="cuda")
+    for accumulate, expect in ((0, want), (1, 2 * want)):
+        _lib.check(lib.mcl_gemm_bf16(a_store.data_ptr(), a_mn, a_store.stride(0), b_store.data_ptr(), b_mn,
+                                     b_store.stride(0), C.data_ptr(), C.stride(0), M, N, K, accumulate,
+                                     ops._stream(C.device)))
+        torch.cuda.synchronize()
+        torch.testing.assert_close(C, expect, rtol=1e-4, atol=1e-3 * K ** 0.5)
+
+
+@pytest.mark.parametrize("Q,V,D,eps,cap", [(700, 9000, 128, 0.1, None), (300, 50000, 64, 0.0, None),
+                                           (5000, 20000, 64, 0.1, None), (260, 3000, 72, 0.0, 6.0),
+                                           (24, 262235, 1152, 0.0, None)])
+def test_f1_native_backward_blocks_and_chunks(Q, V, D, eps, cap):
+    """bf16 backward on the tensor cores across the library's blocking: several row blocks, several
+    table chunks (V beyond one dL/dz block), several blocks of 4096 rows, soft-capped logits, and the
+    reference's own shape (a few labelled rows against the Gemma-3 table).  Reference: torch autograd
+    in fp32 through F.cross_entropy(softcap(h @ E^T)) on the same bf16 values."""
+    from multimodal_concept_learning_b200.autograd import fused_cross_entropy
+    g = torch.Generator(device="cuda").manual_seed(Q + V)
+    h = (torch.randn(Q, D, generator=g, device="cuda") * 0.4).to(torch.bfloat16).requires_grad_(True)
+    E = (torch.randn(V, D, generator=g, device="cuda") * 0.4).to(torch.bfloat16).requires_grad_(True)
+    labels = torch.randint(0, V, (Q,), generator=g, device="cuda")
+    labels[::4] = -100
+    loss, pred = fused_cross_entropy(h, E, labels, label_smoothing=eps, softcap=cap)
+    (loss * 3.0).backward()                                  # a non-trivial upstream gradient
+    h2 = h.detach().float().requires_grad_(True)
+    E2 = E.detach().float().requires_grad_(True)
+    z = h2 @ E2.T
+    if cap:
+        z = torch.tanh(z / cap) * cap
+    ref = F.cross_entropy(z, labels, ignore_index=-100, label_smoothing=eps)
+    (ref * 3.0).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    for got, want in ((h.grad, h2.grad), (E.grad, E2.grad)):
+        scale = want.abs().max()
+        assert (got.float() - want).abs().max() <= 1e-2 * scale, float((got.float() - want).abs().max() / scale)
+    assert (h.grad[::4] == 0).all()
+
+
+def test_f1_backward_uses_no_library_gemm():
+    """'autograd.py contains no torch.mm' -- the backward is the library's own kernels."""
+    import inspect
+    import multimodal_concept_learning_b200.autograd as ag
+    src = inspect.getsource(ag)
+    for banned in ("torch.mm", "torch.matmul", " @ ", "F.linear", "einsum", "torch.bmm"):
+        assert banned not in src, banned
+    import multimodal_concept_learning_b200 as mcl
+    from multimodal_concept_learning_b200.autograd import fused_cross_entropy
+    h = torch.randn(200, 64, device="cuda").bfloat16().requires_grad_(True)
+    E = torch.randn(3000, 64, device="cuda").bfloat16().requires_grad_(True)
+    loss, _ = fused_cross_entropy(h, E, torch.randint(0, 3000, (200,), device="cuda"))
+    n0 = mcl.launch_count()
+    loss.backward()
+    assert mcl.launch_count() - n0 == 3, "dL/dz (scan kernel, grad epilogue) + two tcgen05 GEMMs"
