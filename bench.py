@@ -509,6 +509,53 @@ CPU_SAMPLE_NOTE = ("torch fp32 normalize(q) -> matmul -> topk -> logsumexp/CE on
                    "fp32 normalised table prepared once outside the timed step")
 
 
+def backward_bench(Q, V, D, labelled, device, pk, steps=3):
+    """forward + backward of the fused cross-entropy through the public autograd API
+    (`fused_cross_entropy(...).backward()`): the scan's grad epilogue recomputes dL/dz per tile, two
+    tcgen05 GEMMs form dL/dq and dL/dT.  `labelled` rows carry a label (the others are -100)."""
+    from multimodal_concept_learning_b200.autograd import fused_cross_entropy
+    import multimodal_concept_learning_b200 as mcl
+    g = torch.Generator(device=device).manual_seed(4321)
+    h = (torch.randn(Q, D, generator=g, device=device) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    E = (torch.randn(V, D, generator=g, device=device) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    labels = torch.full((Q,), -100, dtype=torch.long, device=device)
+    rows = torch.linspace(0, Q - 1, labelled, device=device).long()
+    labels[rows] = torch.randint(0, V, (labelled,), generator=g, device=device)
+
+    def step():
+        h.grad = None
+        E.grad = None
+        loss, _ = fused_cross_entropy(h, E, labels)
+        loss.backward()
+        return loss
+    step()
+    torch.cuda.synchronize(device)
+    n0 = mcl.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / steps
+    fwd = 2.0 * Q * V * D                       # the forward scans every row
+    bwd_alg = 4.0 * labelled * V * D            # dL/dq and dL/dT
+    bwd_exec = 6.0 * labelled * V * D           # + the recomputed scores
+    # bytes the backward cannot avoid: the table once, the fp32 table gradient once
+    hbm = (2.0 * V * D + 4.0 * V * D) / (ms * 1e-3) / 1e9
+    out = {"Q": Q, "V": V, "D": D, "labelled_rows": labelled, "ms_fwd_bwd": ms,
+           "alg_tflops": (fwd + bwd_alg) / (ms * 1e-3) / 1e12,
+           "tensor_frac": (fwd + bwd_alg) / (ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+           "executed_tflops": (fwd + bwd_exec) / (ms * 1e-3) / 1e12,
+           "min_hbm_gbs": hbm, "min_hbm_frac": hbm / pk["hbm_gbs"],
+           "gpu_launches": int((mcl.launch_count() - n0) // steps),
+           "what": "fused_cross_entropy(h, E, labels) + loss.backward(): tcgen05 forward scan (k=1), grad-epilogue "
+                   "scan + two tcgen05 GEMMs per dL/dz block; includes the torch glue (row gather, fp32->bf16 casts)"}
+    del h, E
+    torch.cuda.empty_cache()
+    return out
+
+
 def literal_pair_loop_baseline(device_unused=None):
     """BASELINE.md section 4.1 / token_embedding_analysis.py:237-246: the reference's literal
     per-pair sklearn loop for the 16 x 16 self-similarity of the C1 concept embeddings, and the
@@ -674,6 +721,14 @@ def main():
                     sweep.append({"workload": name, "error": f"{type(e).__name__}: {e}"[:200]})
                     torch.cuda.empty_cache()
             out["sweep"] = sweep
+            try:
+                out["backward"] = [
+                    backward_bench(32768, 1048576, 1024, 32768, device, pk),      # configs[4]: every row labelled
+                    backward_bench(1672, 262235, 1152, 24, device, pk),           # the reference's LM head: 3 labels per sample
+                ]
+            except Exception as e:
+                out["backward"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

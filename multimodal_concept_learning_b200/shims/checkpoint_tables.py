@@ -61,9 +61,44 @@ class EpochTables:
     tables: Dict[str, torch.Tensor] = field(default_factory=dict)
     inv_norms: Dict[str, torch.Tensor] = field(default_factory=dict)
 
+    _graphs: Dict[tuple, tuple] = field(default_factory=dict, repr=False)
+
     def scan(self, epoch: str, q: torch.Tensor, k: int, **kw) -> ops.ScanOutput:
         """Cosine top-k / LSE of ``q`` against the table of ``epoch`` using the cached norms."""
         return ops.concept_scan(q, self.tables[epoch], k, inv_norm_t=self.inv_norms[epoch], **kw)
+
+    def scan_all_epochs(self, q: torch.Tensor, k: int, scale: float = 1.0) -> Dict[str, ops.ScanOutput]:
+        """The same concept queries against EVERY epoch's table with one launch from the host: the
+        per-epoch scans (tables on the GPU, cached inverse norms, no extra pass over any table) are
+        captured once per query shape in a CUDA graph and replayed -- the analysis scripts' loop
+        over ``embeddings_by_epoch`` (token_embedding_analysis.py:97-121 loads them, :648-660 walks
+        them) becomes one ``cudaGraphLaunch`` for all epochs.  The returned outputs alias buffers
+        owned by the graph: valid until the next call with the same query shape."""
+        if not self.tables or any(not t.is_cuda for t in self.tables.values()):
+            raise RuntimeError("scan_all_epochs needs the tables on the GPU: load_embeddings_by_epoch(..., device='cuda')")
+        dev = next(iter(self.tables.values())).device
+        key = (tuple(q.shape), q.dtype, int(k), float(scale))
+        if key not in self._graphs:
+            q_static = torch.zeros(q.shape, dtype=q.dtype, device=dev)
+
+            def run():
+                return {name: ops.concept_scan(q_static, t, k, scale=scale, inv_norm_t=self.inv_norms[name])
+                        for name, t in self.tables.items()}
+            with torch.cuda.device(dev):
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):          # one-time work (attributes, tensor maps, plans) outside the capture
+                    run()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = run()
+            self._graphs[key] = (graph, q_static, outs)
+        graph, q_static, outs = self._graphs[key]
+        q_static.copy_(q, non_blocking=True)
+        graph.replay()
+        return outs
 
 
 def load_embeddings_by_epoch(results_dir: str, device: Optional[str] = None,

@@ -62,3 +62,26 @@ def test_gpu_tables_cache_inverse_norms(tmp_path, lib_built):
     out = res.scan("epoch_0", q, 10)
     ref = R.concept_scan_ref(table[:20], table, 10, keep_scores=True)
     check_topk(out.topk_val, out.topk_idx, ref.scores, 10, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_all_epochs_in_one_graph_launch(tmp_path, lib_built):
+    """SURVEY 8f-3, second half: the queries against every epoch's table with ONE launch from the
+    host (a CUDA graph over the per-epoch scans); results equal the per-epoch scans, also when the
+    graph is replayed with new queries."""
+    models = tmp_path / "models"
+    models.mkdir()
+    tables = {}
+    for name, seed in (("initial_model.pt", 1), ("epoch_0_model.pt", 2), ("epoch_1_model.pt", 3), ("epoch_2_model.pt", 4)):
+        sd, tables[name] = _state_dict(seed, V=5000, D=64)
+        torch.save(sd, models / name)
+    res = load_embeddings_by_epoch(str(tmp_path), device="cuda", verbose=False)
+    for seed in (7, 8):
+        q = torch.randn(24, 64, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16).cuda()
+        outs = res.scan_all_epochs(q, 10)
+        assert list(outs) == ["initial", "epoch_0", "epoch_1", "epoch_2"]
+        for name, out in outs.items():
+            want = res.scan(name, q, 10)
+            assert torch.equal(out.topk_idx, want.topk_idx) and torch.equal(out.topk_val, want.topk_val)
+            torch.testing.assert_close(out.stats, want.stats, rtol=0, atol=0)
+    assert len(res._graphs) == 1
