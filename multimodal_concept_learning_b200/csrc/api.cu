@@ -11,6 +11,7 @@
 #include "kernels.h"
 
 using namespace mcl;
+namespace mcl { extern std::atomic<int> g_gather_variant; }
 
 namespace {
 
@@ -862,6 +863,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 14) return g_opt_notop1.exchange(value);
   if (opt == 15) return g_opt_filter.exchange(value);
   if (opt == 16) return g_opt_noqnorm.exchange(value);
+  if (opt == 17) return g_gather_variant.exchange((int)value);
   if (opt == 103) return drift_timeouts_total();
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;

@@ -9,6 +9,8 @@
 
 namespace mcl {
 
+std::atomic<int> g_gather_variant{0};   // library option 17 (A/B of the gather kernel's register cap)
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 row_inv_norm_kernel(const T* __restrict__ x, long long rows, int dim, long long ld,
@@ -83,7 +85,8 @@ gather_mean_kernel(const T* __restrict__ table, long long V, int D, long long ld
 
 // (Measured on B200, profiles/r02_gather_mean_ncu_raw.csv: 2.3 TB/s = 0.36 of the copy peak for 1-4
 // ids per row at D = 3584 -- 168 registers leave 12 warps per SM, and a row is a chain of dependent
-// round trips (offsets -> id -> row), so the bytes in flight, not the DRAM, bound it.  A staging
+// round trips (offsets -> id -> row), so the bytes in flight, not the DRAM, bound it; the kernel
+// below therefore runs persistent warps that prefetch the next row's CSR entries.  A staging
 // ring fed by cp.async.bulk with a single issuing thread was tried and measured SLOWER (1.2 TB/s,
 // the consumers' per-row latency moved into the producer's slot waits) and was removed.)
 // Register-resident variant for rows of at most 32 * NV 16-byte vectors (D <= 4096 bf16 with
@@ -92,75 +95,91 @@ gather_mean_kernel(const T* __restrict__ table, long long V, int D, long long ld
 // pass -- and a lane has NV independent 16-byte loads in flight per gathered row (a gather is
 // latency-bound: few warps fit at this register count, so the parallelism has to come from inside
 // the thread).  Same arithmetic, same order: bit-identical outputs.
-template <typename T, int NV>
-__global__ void __launch_bounds__(128)
+template <typename T, int NV, int MB>
+__global__ void __launch_bounds__(128, MB)
 gather_mean_reg_kernel(const T* __restrict__ table, long long V, int D, long long ld,
                        const long long* __restrict__ offsets, const long long* __restrict__ ids,
                        long long Q, int normalize, T* __restrict__ out, long long ld_out,
                        int* __restrict__ bad_flag) {
   constexpr int N = Vec<T>::N;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= Q) return;
-  const long long b = offsets[row], e = offsets[row + 1];
-  const int n = (int)(e - b);
-  const float fn = (float)(n > 0 ? n : 1);
   const int nvec = D / N;
   const int ntail = D - nvec * N;                  // < N ragged columns: lane c owns column nvec*N + c
-  T* o = out + row * ld_out;
-  float acc[NV][N];
-  float tail = 0.f;
+  // Persistent warps over rows w, w + W, ...  A row is a chain of dependent round trips
+  // (offsets -> ids -> table rows): the NEXT row's offsets are requested before this row is
+  // processed and its first 32 ids (one coalesced load) once this row's table loads are in flight,
+  // so that only the table-row latency is exposed per row.
+  const long long W = (long long)gridDim.x * 4;
+  long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  long long b = 0, e = 0, my_id = 0;
+  if (row < Q) {
+    b = __ldg(offsets + row); e = __ldg(offsets + row + 1);
+    if (lane < e - b) my_id = __ldg(ids + b + lane);
+  }
+  for (; row < Q; row += W) {
+    const long long next = row + W;
+    long long nb = 0, ne = 0, next_id = 0;
+    if (next < Q) { nb = __ldg(offsets + next); ne = __ldg(offsets + next + 1); }
+    const int n = (int)(e - b);
+    const float fn = (float)(n > 0 ? n : 1);
+    T* o = out + row * ld_out;
+    float acc[NV][N];
+    float tail = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int c = 0; c < N; ++c) acc[i][c] = 0.f;
-  for (long long j = b; j < e; ++j) {
-    long long id = __ldg(ids + j);
-    if (id < 0 || id >= V) { if (bad_flag) *bad_flag = 1; id = id < 0 ? 0 : V - 1; }
-    const T* src = table + id * ld;
-    uint4 raw[NV];                                 // all loads of the row first, widened on use
+      for (int c = 0; c < N; ++c) acc[i][c] = 0.f;
+    for (long long j = b; j < e; ++j) {
+      long long id = (j - b < 32) ? __shfl_sync(0xffffffffu, my_id, (int)(j - b)) : __ldg(ids + j);
+      if (id < 0 || id >= V) { if (bad_flag) *bad_flag = 1; id = id < 0 ? 0 : V - 1; }
+      const T* src = table + id * ld;
+      uint4 raw[NV];                               // all loads of the row first, widened on use
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        raw[i] = (v < nvec) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)v * N)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (lane < ntail) tail += Vec<T>::ld1(src + nvec * N + lane);
+      if (j == b && lane < ne - nb) next_id = __ldg(ids + nb + lane);   // (nb / ne have landed by now)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float a[N];
+        Vec<T>::widen(raw[i], a);
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc[i][c] += a[c];   // (+0 past nvec)
+      }
+    }
+    if (n == 0 && lane < ne - nb) next_id = __ldg(ids + nb + lane);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        acc[i][c] = acc[i][c] / fn;
+        ss = fmaf(acc[i][c], acc[i][c], ss);       // (vectors past nvec hold zeros)
+      }
+    }
+    tail = tail / fn;
+    float inv = 1.f;
+    if (normalize) {
+      if (lane < ntail) ss = fmaf(tail, tail, ss);
+      const float nrm = sqrtf(warp_sum(ss));
+      inv = (nrm < kTinyNorm) ? 1.0f : 1.0f / nrm;
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
-      raw[i] = (v < nvec) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)v * N)) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (lane < ntail) tail += Vec<T>::ld1(src + nvec * N + lane);
+      if (v < nvec) {
+        if (normalize) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float a[N];
-      Vec<T>::widen(raw[i], a);
-#pragma unroll
-      for (int c = 0; c < N; ++c) acc[i][c] += a[c];   // (+0 past nvec)
-    }
-  }
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-      acc[i][c] = acc[i][c] / fn;
-      ss = fmaf(acc[i][c], acc[i][c], ss);         // (vectors past nvec hold zeros)
-    }
-  }
-  tail = tail / fn;
-  float inv = 1.f;
-  if (normalize) {
-    if (lane < ntail) ss = fmaf(tail, tail, ss);
-    const float nrm = sqrtf(warp_sum(ss));
-    inv = (nrm < kTinyNorm) ? 1.0f : 1.0f / nrm;
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
-      if (normalize) {
-#pragma unroll
-        for (int c = 0; c < N; ++c) acc[i][c] *= inv;
+          for (int c = 0; c < N; ++c) acc[i][c] *= inv;
+        }
+        Vec<T>::store(o + (size_t)v * N, acc[i]);
       }
-      Vec<T>::store(o + (size_t)v * N, acc[i]);
     }
+    if (lane < ntail) Vec<T>::st1(o + nvec * N + lane, normalize ? tail * inv : tail);
+    b = nb; e = ne; my_id = next_id;
   }
-  if (lane < ntail) Vec<T>::st1(o + nvec * N + lane, normalize ? tail * inv : tail);
 }
 
 // Cross-entropy from the scan's row statistics (m, s, sum_z, z_label): per row
@@ -232,13 +251,23 @@ static cudaError_t launch_gather_mean_t(const T* table, int64_t V, int64_t D, in
                                         const int64_t* ids, int64_t Q, int normalize, T* out, int64_t ld_out,
                                         int* bad_flag, cudaStream_t s) {
   const int64_t nvec = D / Vec<T>::N;
-  const unsigned grid4 = (unsigned)((Q + 3) / 4);
-#define MCL_GM_REG(NV)                                                                              \
-  gather_mean_reg_kernel<T, NV><<<grid4, 128, 0, s>>>(table, V, (int)D, ld, (const long long*)offsets, \
-                                                      (const long long*)ids, Q, normalize, out, ld_out, bad_flag)
-  if (nvec <= 32 * 4) MCL_GM_REG(4);
-  else if (nvec <= 32 * 8) MCL_GM_REG(8);
-  else if (nvec <= 32 * 16) MCL_GM_REG(16);
+  int dev = 0, sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  // persistent warps: as many blocks as fit the chip at this kernel's register count
+#define MCL_GM_REG(NV, MB)                                                                          \
+  do {                                                                                              \
+    int occ = 1;                                                                                    \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_mean_reg_kernel<T, NV, MB>, 128, 0); \
+    const long long want = (Q + 3) / 4, fit = (long long)sm * (occ > 0 ? occ : 1);                  \
+    gather_mean_reg_kernel<T, NV, MB><<<(unsigned)(want < fit ? want : fit), 128, 0, s>>>(          \
+        table, V, (int)D, ld, (const long long*)offsets, (const long long*)ids, Q, normalize, out, ld_out, bad_flag); \
+  } while (0)
+  // minimum blocks per SM = the register cap: 8 / 5 / 3 blocks of four warps keep the accumulators of
+  // NV vectors per lane in registers (g_gather_variant = 1: two blocks, 255 registers, no spills -- A/B)
+  if (nvec <= 32 * 4) MCL_GM_REG(4, 8);
+  else if (nvec <= 32 * 8) MCL_GM_REG(8, 5);
+  else if (nvec <= 32 * 16) { if (g_gather_variant.load()) MCL_GM_REG(16, 2); else MCL_GM_REG(16, 3); }
   else
     gather_mean_kernel<T><<<(unsigned)((Q + 7) / 8), 256, 0, s>>>(table, V, (int)D, ld, (const long long*)offsets,
                                                                  (const long long*)ids, Q, normalize, out, ld_out,

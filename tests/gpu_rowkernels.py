@@ -35,10 +35,13 @@ def main():
             lens = torch.randint(lo, hi, (Q,), generator=g, device="cuda")
             offs = torch.cat([torch.zeros(1, dtype=torch.long, device="cuda"), lens.cumsum(0)])
             ids = torch.randint(0, V, (int(offs[-1]),), generator=g, device="cuda")
-            ms = timed(lambda: mcl.gather_mean(table, offs, ids, norm, validate=False))
             b = ids.numel() * D * 2 + Q * D * 2 + ids.numel() * 8 + (Q + 1) * 8
-            print(f"gather_mean V={V} D={D} Q={Q} ids/row in [{lo},{hi}) normalize={norm}: {ms * 1e3:.1f} us, "
-                  f"{b / ms / 1e6:.0f} GB/s ({b / 1e6:.0f} MB)")
+            for variant in (0, 1):
+                old = mcl.set_option(17, variant)
+                ms = timed(lambda: mcl.gather_mean(table, offs, ids, norm, validate=False))
+                mcl.set_option(17, old)
+                print(f"gather_mean[v{variant}] V={V} D={D} Q={Q} ids/row in [{lo},{hi}) normalize={norm}: {ms * 1e3:.1f} us, "
+                      f"{b / ms / 1e6:.0f} GB/s ({b / 1e6:.0f} MB)")
         del table
 
 
