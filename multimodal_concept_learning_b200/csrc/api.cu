@@ -19,7 +19,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_ctas{0}, g_opt_g{0}, g_opt_simt{0}, g_opt_timing{0}, g_opt_cluster{0}, g_opt_allgather{0}, g_opt_phase{0};
 std::atomic<long long> g_opt_leftover{1}, g_opt_segpen{1}, g_opt_l2{0}, g_opt_win{0}, g_opt_nosmall{0}, g_opt_joint{0};
-std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0}, g_opt_filter{0}, g_opt_noqnorm{0};
+std::atomic<long long> g_opt_noseed{0}, g_opt_notop1{0}, g_opt_filter{0}, g_opt_noqnorm{0}, g_opt_nopanel{0};
 
 PlanKnobs knobs() {
   PlanKnobs k;
@@ -91,7 +91,7 @@ bool use_tc(int dtype) { return dtype == MCL_DTYPE_BF16 && !g_opt_simt.load(); }
 struct ScanLayout {
   bool tc; TcPlan plan; int nsplit, nslots, rows_padded, nctr;
   // small-batch path (select.cu): one row block, scores dumped [Q][small_ld] + per-range lists
-  bool small; int64_t small_ld; int splits; size_t scores_bytes, extra_bytes;
+  bool small; int64_t small_ld, gld; int splits; size_t scores_bytes, gmax_bytes, extra_bytes;
   int mode;            // epilogue mode of the tcgen05 scan: top-k / top-1 (k == 1)
   // threshold seeding pre-pass (scan_tc_kernel.cuh, kModeSeed): seed_tiles sample tiles, every
   // seed_stride-th tile of the table, scanned with a plan of their own
@@ -132,8 +132,14 @@ ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int k, int dtype, int sm
     if (L.small) {
       L.splits = select_splits(V);
       // lists sized for k = MCL_MAX_K: the workspace query does not depend on k
-      L.extra_bytes = L.scores_bytes + ((((size_t)L.splits * Q * MCL_MAX_K * 4) + 255) & ~(size_t)255) +
-                      (size_t)L.splits * Q * MCL_MAX_K * 8;
+      const size_t lists = ((((size_t)L.splits * Q * MCL_MAX_K * 4) + 255) & ~(size_t)255) +
+                           (size_t)L.splits * Q * MCL_MAX_K * 8;
+      // one-launch path (panel_scan.cu): keys of the maxima of 32 consecutive scores, [Q][gld], and
+      // the CTAs' partial statistics, [sm][Q] float4 -- in the place of the two-kernel path's lists
+      L.gld = (((V + 127) / 128) * 4 + 31) / 32 * 32;
+      L.gmax_bytes = (((size_t)Q * L.gld * sizeof(uint32_t)) + 255) & ~(size_t)255;
+      const size_t panel = L.gmax_bytes + (size_t)sm * Q * 16;
+      L.extra_bytes = L.scores_bytes + std::max(lists, panel);
     }
   } else {
     L.nsplit = simt_nsplit(Q, V, sm);
@@ -184,7 +190,11 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   // MCL_SCAN_NORMALIZE_Q: the library forms 1/||q_row|| itself -- inside the scan kernel for small
   // batches (no extra launch), else with the row kernel into a workspace scratch
   const bool want_qnorm = (flags & MCL_SCAN_NORMALIZE_Q) && !inv_q;
-  const bool qnorm_in_kernel = want_qnorm && L.tc && dtype == MCL_DTYPE_BF16 && Q <= 64 && !g_opt_noqnorm.load();
+  // One-row-block batches: ONE launch (panel_scan.cu: table panels on the M side, scores dumped to
+  // the workspace, grid barrier, exact selection); option 18 restores the two-kernel path
+  // (scan_tc_kernel with the filter off + row_select_kernel) for A/B measurements.
+  const bool panel = L.small && !dbg && !g_opt_nopanel.load();
+  const bool qnorm_in_kernel = want_qnorm && L.tc && dtype == MCL_DTYPE_BF16 && (panel || Q <= 64) && !g_opt_noqnorm.load();
   if (want_qnorm && !qnorm_in_kernel) {
     cudaError_t e0 = launch_row_inv_norm(q, dtype, Q, D, ldq, ws.inv_q, stream);
     if (e0 != cudaSuccess) return cuda_fail(e0, "row_inv_norm launch (queries)");
@@ -208,6 +218,16 @@ int scan_impl(const void* q, const void* table, int dtype, int64_t Q, int64_t V,
   }
   SlotMap map{};
   cudaError_t e;
+  if (panel) {
+    char msg[256] = "";
+    a.small_scores = nullptr;
+    char* x = (char*)ws.extra + L.scores_bytes;
+    e = launch_panel_scan(a, di.sm, (float*)ws.extra, L.small_ld, (uint32_t*)x, L.gld, (float*)(x + L.gmax_bytes),
+                          topk_val, topk_idx, row_stats, stream, msg, sizeof(msg));
+    if (e != cudaSuccess) return fail(MCL_ERR_CUDA, "panel scan launch: %s %s", cudaGetErrorString(e), msg);
+    g_launches++;
+    return MCL_OK;
+  }
   const bool phases = g_opt_phase.load() != 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (phases) {
@@ -864,7 +884,9 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 15) return g_opt_filter.exchange(value);
   if (opt == 16) return g_opt_noqnorm.exchange(value);
   if (opt == 17) return g_gather_variant.exchange((int)value);
+  if (opt == 18) return g_opt_nopanel.exchange(value);
   if (opt == 103) return drift_timeouts_total();
+  if (opt == 104) return panel_barrier_faults();
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns
   return -1;
 }

@@ -106,6 +106,11 @@ cudaError_t launch_select_small(const float* scores, int64_t ld, int64_t V, int6
                                 const SlotView& sv, const SlotMap& map, float* list_val,
                                 int64_t* list_idx, void* row_ctr, int64_t index_base, float* topk_val,
                                 int64_t* topk_idx, float* row_stats, cudaStream_t s);
+// One-row-block batches in one launch (panel_scan.cu): scores [Q][ld] scratch -> final outputs.
+cudaError_t launch_panel_scan(const ScanArgs& a, int sm_count, float* scores, int64_t ld, uint32_t* gmax,
+                              int64_t gld, float* part, float* topk_val,
+                              int64_t* topk_idx, float* row_stats, cudaStream_t s, char* err, size_t errlen);
+long long panel_barrier_faults();   // grid-barrier waits of the panel scan that gave up (all devices)
 // R per-shard results (rank r's arrays start r * stride bytes after the base) -> final
 cudaError_t launch_merge_ranks(const float* val, const int64_t* idx, const float* stats,
                                size_t val_stride, size_t idx_stride, size_t stats_stride, int R,

@@ -124,11 +124,13 @@ def _(stats, labels, label_smoothing, vocab):
     return stats.new_empty(stats.shape[0]), stats.new_empty(2)
 
 
-@torch.library.custom_op("mcl::concept_scan", mutates_args=(), device_types="cuda")
-def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
-                     inv_norm_t: Optional[Tensor], labels: Optional[Tensor], scale: float,
-                     k: int, index_base: int, softcap: float = 0.0,
-                     normalize_q: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+_WS_BYTES: dict = {}     # (device index, Q, V, D, k, dtype code) -> workspace bytes (a pure function of these)
+
+
+def _concept_scan_impl(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
+                       inv_norm_t: Optional[Tensor], labels: Optional[Tensor], scale: float,
+                       k: int, index_base: int, softcap: float = 0.0,
+                       normalize_q: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     lib = load()
     dev = q.device
     Q, D = q.shape
@@ -138,7 +140,10 @@ def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
     idx = torch.empty((Q, k), dtype=torch.int64, device=dev)
     stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        ws_bytes = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
+        key = (dev.index, Q, V, D, k, code)
+        ws_bytes = _WS_BYTES.get(key)
+        if ws_bytes is None:
+            ws_bytes = _WS_BYTES[key] = lib.mcl_scan_workspace_bytes(Q, V, D, k, code)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         # normalize_q without caller-supplied norms: the library forms them (inside the scan kernel
         # for small batches -- MCL_SCAN_NORMALIZE_Q)
@@ -149,6 +154,11 @@ def _concept_scan_op(q: Tensor, table: Tensor, inv_norm_q: Optional[Tensor],
                                       idx.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, flags,
                                       _stream(dev)))
     return val, idx, stats
+
+
+# the custom op is what torch.compile / export see; eager calls go straight to the function (the
+# op dispatcher costs ~15 us per call, more than half of a small-batch scan's GPU time)
+_concept_scan_op = torch.library.custom_op("mcl::concept_scan", mutates_args=(), device_types="cuda")(_concept_scan_impl)
 
 
 @_concept_scan_op.register_fake
@@ -289,9 +299,9 @@ def concept_scan(q: Tensor, table: Tensor, k: int, *, normalize_q: bool = True,
         labels = labels.to(device=dev, dtype=torch.int64).contiguous()
     if softcap is not None and not softcap > 0:
         raise ValueError("softcap must be > 0 (or None)")
-    val, idx, stats = torch.ops.mcl.concept_scan(q, table, inv_norm_q, inv_norm_t, labels,
-                                                 float(scale), int(k), int(index_base),
-                                                 float(softcap or 0.0), bool(normalize_q))
+    scan = torch.ops.mcl.concept_scan if torch.compiler.is_compiling() else _concept_scan_impl
+    val, idx, stats = scan(q, table, inv_norm_q, inv_norm_t, labels, float(scale), int(k), int(index_base),
+                           float(softcap or 0.0), bool(normalize_q))
     return ScanOutput(val, idx, stats, int(vocab_total or table.shape[0]), labels,
                       float(label_smoothing))
 
@@ -401,6 +411,7 @@ def merge(val: Tensor, idx: Tensor, stats: Tensor) -> Tuple[Tensor, Tensor, Tens
 
 
 def set_option(opt: int, value: int) -> int:
+    _WS_BYTES.clear()          # plan knobs change the workspace a scan needs
     return int(load().mcl_set_option(opt, value))
 
 

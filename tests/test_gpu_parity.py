@@ -384,47 +384,124 @@ def test_graphed_scan_equals_direct_scan(mcl, Q, with_labels):
 
 
 @pytest.mark.parametrize("Q,V,D,k", [(16, 50257, 768, 50), (96, 20000, 1152, 64), (128, 6144, 64, 50),
-                                     (5, 6145, 72, 7), (1, 300, 8, 1)])
+                                     (5, 6145, 72, 7), (1, 300, 8, 1), (17, 9001, 136, 33), (33, 130, 64, 64),
+                                     (65, 70000, 256, 50)])
 def test_small_batch_path_equals_streaming_path(mcl, Q, V, D, k):
-    """One-row-block batches take the score-dump + radix-select path (select.cu); option 11
-    sends them through the streaming top-k filter instead.  Same scores, same tie rule: the
-    outputs must be bit-identical, and match the oracle."""
+    """One-row-block batches take the one-launch panel path (panel_scan.cu: score dump, grid
+    barrier, exact selection); option 18 sends them through the two-kernel path (scan with the
+    filter off + select.cu) and option 11 through the streaming top-k filter.  Same scores, same
+    tie rule: the top-k must be bit-identical on all three, the statistics agree to fp32
+    summation order, and everything matches the oracle."""
     q, t = make_inputs(Q, V, D, 70 + Q)
     t[V // 2] = t[3]                                   # an exact duplicate: the lower row must win
     labels = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(Q))
     qd, td = q.cuda(), t.cuda()
+    n0 = mcl.launch_count()
     a = mcl.concept_scan(qd, td, k, scale=25.0, labels=labels, label_smoothing=0.1)
-    old = mcl.set_option(11, 1)
-    try:
-        b = mcl.concept_scan(qd, td, k, scale=25.0, labels=labels, label_smoothing=0.1)
-    finally:
-        mcl.set_option(11, old)
-    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
-    torch.testing.assert_close(a.stats, b.stats, rtol=1e-6, atol=1e-6)
+    launches = mcl.launch_count() - n0
+    if k > 1:                                          # (k = 1 takes the running-argmax epilogue)
+        assert launches == 2, "table row norms + ONE panel-scan launch (query norms in-kernel)"
+    outs = []
+    for opt in (18, 11):
+        old = mcl.set_option(opt, 1)
+        try:
+            outs.append(mcl.concept_scan(qd, td, k, scale=25.0, labels=labels, label_smoothing=0.1))
+        finally:
+            mcl.set_option(opt, old)
+    for b in outs:
+        assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+        torch.testing.assert_close(a.stats[:, 0], b.stats[:, 0], rtol=0, atol=0)     # the row maximum
+        torch.testing.assert_close(a.stats[:, 3], b.stats[:, 3], rtol=0, atol=0)     # the label's score
+        torch.testing.assert_close(a.stats, b.stats, rtol=1e-5, atol=1e-3)           # sums: order of addition
+    assert mcl.set_option(104, 0) == 0, "a grid-barrier wait of the panel scan gave up"
     if Q * V <= 2_000_000:
         ref = R.concept_scan_ref(q, t, k, scale=25.0, labels=labels, label_smoothing=0.1, keep_scores=True)
         check_topk(a.topk_val, a.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-4)
         check_stats(a.stats, ref, rtol=RTOL, atol=1e-3)
 
 
-def test_small_batch_selection_fallback_and_ties(mcl):
-    """Adversarial layout for the selection kernel's thread-maxima bound: 56 of the 256 column
-    classes (mod 256) hold all the large scores, so the bound keeps > 1024 keys and the exact
-    radix select runs; large scores repeat across classes, so the top-k is decided by the
-    lowest-row tie rule.  Raw dot products of bf16-exact integers: the expected answer is exact."""
+@pytest.mark.parametrize("two_kernel", [0, 1])
+@pytest.mark.parametrize("layout", ["mod256", "vec512"])
+def test_small_batch_selection_fallback_and_ties(mcl, two_kernel, layout):
+    """Adversarial layouts for the selection's thread-maxima bound.  "mod256": 56 of the 256 column
+    classes (mod 256) hold all the large scores -- the two-kernel path's bound keeps > 1024 keys;
+    "vec512": the large scores sit in the columns of 8 of the panel path's 512 threads (column c
+    lives in thread (c / 4) % 512), so 15 of its 16 warps see small scores only, the bound keeps
+    > 2048 keys and its exact radix select runs.  Large scores repeat, so the top-k is decided by
+    the lowest-row tie rule.  Raw dot products of bf16-exact integers: the expected answer is exact."""
     V, D, k = 3 * 6144 + 77, 16, 64
     j = torch.arange(V)
-    val = torch.where((j % 256) < 56, 100.0 + (j // 256).float(), (j % 5).float())   # < 256: exact in bf16
+    if layout == "mod256":
+        val = torch.where((j % 256) < 56, 100.0 + (j // 256).float(), (j % 5).float())   # < 256: exact in bf16
+    else:
+        val = torch.where(((j // 4) % 512) < 8, 100.0 + (j // 2048).float(), (j % 5).float())
     t = torch.zeros(V, D)
     t[:, 0] = val
     q = torch.zeros(3, D)
     q[:, 0] = torch.tensor([1.0, 2.0, -1.0])
-    out = mcl.concept_scan(q.bfloat16().cuda(), t.bfloat16().cuda(), k, normalize_q=False, normalize_t=False)
+    old = mcl.set_option(18, two_kernel)
+    try:
+        out = mcl.concept_scan(q.bfloat16().cuda(), t.bfloat16().cuda(), k, normalize_q=False, normalize_t=False)
+    finally:
+        mcl.set_option(18, old)
     for r, mult in enumerate([1.0, 2.0, -1.0]):
         sc = (val * mult).double()
         order = sorted(range(V), key=lambda c: (-sc[c].item(), c))[:k]
         assert out.topk_idx[r].cpu().tolist() == order, f"row {r}"
         torch.testing.assert_close(out.topk_val[r].cpu().double(), sc[order], rtol=0, atol=0)
+        lse = torch.logsumexp(sc, 0)
+        got = out.stats[r, 0].double().cpu() + torch.log(out.stats[r, 1].double().cpu())
+        torch.testing.assert_close(got, lse, rtol=1e-5, atol=1e-5)
+
+
+def test_panel_scan_counters_reset_and_constant_rows(mcl):
+    """The panel scan's grid barrier leaves its two counters at zero: back-to-back launches with
+    different grids (V) and query counts give the answers of fresh launches.  A table of identical
+    rows (every score equal: all V keys survive any bound) takes the radix select and returns rows
+    0 .. k-1."""
+    shapes = [(16, 50257, 64, 50), (3, 300, 64, 5), (128, 20000, 64, 64), (16, 50257, 64, 50), (40, 129, 64, 10)]
+    first = {}
+    for rep in range(2):
+        for i, (Q, V, D, k) in enumerate(shapes):
+            q, t = make_inputs(Q, V, D, 300 + i)
+            out = mcl.concept_scan(q.cuda(), t.cuda(), k, scale=10.0)
+            if rep == 0:
+                first[i] = (out.topk_idx.clone(), out.topk_val.clone(), out.stats.clone())
+                if Q * V <= 2_000_000:
+                    ref = R.concept_scan_ref(q, t, k, scale=10.0, keep_scores=True)
+                    check_topk(out.topk_val, out.topk_idx, ref.scores, k, rtol=RTOL, atol=1e-4)
+            else:
+                assert torch.equal(out.topk_idx, first[i][0]) and torch.equal(out.topk_val, first[i][1])
+                assert torch.equal(out.stats, first[i][2])
+    t = torch.ones(5000, 32).bfloat16().cuda()
+    out = mcl.concept_scan(torch.ones(4, 32).bfloat16().cuda(), t, 50, normalize_q=False, normalize_t=False)
+    assert (out.topk_idx.cpu() == torch.arange(50).expand(4, 50)).all() and (out.topk_val == 32.0).all()
+    torch.testing.assert_close(out.stats[:, 1].cpu(), torch.full((4,), 5000.0), rtol=1e-6, atol=0)
+    assert mcl.set_option(104, 0) == 0
+
+
+@pytest.mark.parametrize("Q,cap", [(16, 8.0), (70, 30.0)])
+def test_panel_scan_softcap_and_shard_base(mcl, Q, cap):
+    """Soft-capped logits and a shard's index base through the one-launch path, against the
+    two-kernel path (bit-identical) and the oracle."""
+    V, D, k = 7001, 200, 20
+    q, t = make_inputs(Q, V, D, 400 + Q)
+    labels = torch.randint(1000, 1000 + V, (Q,), generator=torch.Generator().manual_seed(Q))
+    labels[::4] = -100
+    kw = dict(normalize_q=False, normalize_t=False, labels=labels, softcap=cap, index_base=1000)
+    a = mcl.concept_scan(q.cuda(), t.cuda(), k, **kw)
+    old = mcl.set_option(18, 1)
+    try:
+        b = mcl.concept_scan(q.cuda(), t.cuda(), k, **kw)
+    finally:
+        mcl.set_option(18, old)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+    torch.testing.assert_close(a.stats, b.stats, rtol=1e-5, atol=1e-3)
+    local = torch.where(labels == -100, labels, labels - 1000)
+    ref = R.concept_scan_ref(q, t, k, normalize_q=False, normalize_t=False, labels=local, softcap=cap,
+                             keep_scores=True)
+    check_topk(a.topk_val, a.topk_idx - 1000, ref.scores, k, rtol=RTOL, atol=1e-4)
+    check_stats(a.stats, ref, rtol=RTOL, atol=1e-3)
 
 
 # ---- edge cases of the domain -----------------------------------------------------------
@@ -477,7 +554,9 @@ def test_top1_epilogue_equals_general_path_and_oracle(mcl, Q, V, D, cap):
     finally:
         mcl.set_option(14, old)
     assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
-    torch.testing.assert_close(a.stats, b.stats, rtol=1e-6, atol=1e-6)
+    # (sums in a different order of addition: one-row-block batches take the panel path under option 14)
+    torch.testing.assert_close(a.stats[:, [0, 3]], b.stats[:, [0, 3]], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(a.stats, b.stats, rtol=1e-5, atol=1e-3)
     ref = R.concept_scan_ref(q, t, 1, normalize_q=False, normalize_t=False, labels=labels,
                              label_smoothing=0.1, softcap=cap, keep_scores=True)
     check_topk(a.topk_val, a.topk_idx, ref.scores, 1, rtol=RTOL, atol=1e-4)
