@@ -49,6 +49,10 @@ WORKLOADS = {
     # Gemma-3 table after the OOD tokens were added), raw dot product, CE + argmax (multimodal_training.py:276)
     "gemma3_head": dict(Q=1672, V=262235, D=1152, normalize=False, scale=1.0, labels=True, k=1, cfg=None,
                         desc="reference-native LM head: 1672 hidden states x Gemma-3 table 262235x1152, CE + argmax (k=1)"),
+    # ... and its evaluation with label-aware row selection (shims/mllm.py rows="labelled"): the 3 answer
+    # positions of each of 8 samples (multimodal_training.py:276-285 reads no other row), one row block
+    "gemma3_eval": dict(Q=24, V=262235, D=1152, normalize=False, scale=1.0, labels=True, k=1, cfg=None,
+                        desc="reference-native evaluation, labelled rows only: 24 hidden states x Gemma-3 table 262235x1152, CE + argmax (k=1)"),
 }
 K_TOP = 50
 METRIC = "concept queries/sec vs vocab (top-k=50)"
@@ -70,12 +74,12 @@ def peaks():
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
-def ncu_traffic(workload, world):
+def ncu_traffic(workload, world, kernel="scan_tc"):
     """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, per
     launch, from the newest committed `ncu --set full` raw page of this workload
-    (profiles/r*_<workload>[_nN]_scan_tc*_ncu_raw.csv).  None when no capture exists."""
+    (profiles/r*_<workload>[_nN]_<kernel>*_ncu_raw.csv).  None when no capture exists."""
     tag = workload if world == 1 else f"{workload}_n{world}"
-    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", f"r*_{tag}_scan_tc*_ncu_raw.csv"))
+    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", f"r*_{tag}_{kernel}*_ncu_raw.csv"))
              if world > 1 or not re.search(r"_n\d+_", os.path.basename(f))]
     if not files:
         return None, None
@@ -86,7 +90,7 @@ def ncu_traffic(workload, world):
         ik, ir, iw = head.index("Kernel Name"), head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
         # (the main scan kernel: epilogue modes 0 / 1; mode 2 is the threshold-seeding pre-pass)
         vals = [float(r[ir]) * _UNIT[units[ir]] + float(r[iw]) * _UNIT[units[iw]] for r in rows[2:]
-                if re.search(r"scan_tc_kernel<\d, \d(, [01])?>", r[ik])]
+                if re.search(r"scan_tc_kernel<\d, \d(, [01])?>|panel_scan_kernel", r[ik])]
         if not vals:
             return None, None
         return sum(vals) / len(vals), os.path.relpath(path, ROOT)
@@ -148,7 +152,7 @@ def make_inputs(w, device, rank, world, seed_base=1234):
     g = torch.Generator(device=device).manual_seed(seed_base + cfg)
     q = torch.randn(w["Q"], w["D"], generator=g, device=device).to(torch.bfloat16)
     labels = torch.randint(0, w["V"], (w["Q"],), generator=g, device=device) if w["labels"] else None
-    if w["k"] == 1 and labels is not None:
+    if w["k"] == 1 and labels is not None and w["Q"] >= 209:
         # answer-only supervision (imagenet_dataset.py:171-175): 1-3 labelled positions per sample of 209
         keep = torch.zeros(w["Q"], dtype=torch.bool, device=device)
         keep[torch.arange(205, w["Q"], 209, device=device)] = True
@@ -618,7 +622,9 @@ def main():
             "config": {"workload": f"{cfg_name}: {w['desc']}", "Q": w["Q"],
                        "V": w["V"], "D": w["D"], "k": w["k"],
                        "parallelism": f"vocab-row sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (table {:.2f} GB vs 126 MB)".format(w["V"] * w["D"] * 2 / 1e9)}}
+                       "l2": ("inputs larger than L2 (table {:.2f} GB vs 126 MB)" if w["V"] * w["D"] * 2 > 126e6 else
+                              "table {:.2f} GB fits in the 126 MB L2: ms_per_step is warm, roofline.cold_l2 after a 256 MB flush"
+                              ).format(w["V"] * w["D"] * 2 / 1e9)}}
 
     if args.impl == "reference":
         if rank != 0:
@@ -659,16 +665,32 @@ def main():
                 "parity_check": res.get("parity_check")})
     shard_flops = 2.0 * w["Q"] * w["V"] * w["D"] / world
     achieved = shard_flops / (res["ms_per_step"] * 1e-3) / 1e12
-    traffic, traffic_src = ncu_traffic(args.workload, world)
-    out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                       "frac": achieved / pk["bf16_tflops"], "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],
-                       "peak_source": pk["source"] + " (burst cuBLAS bf16)",
-                       # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, one launch of this
-                       # workload, read from the committed ncu --set full raw page named in traffic_source
-                       "traffic": traffic, "traffic_source": traffic_src,
-                       "traffic_unit": "bytes per launch (algorithmic: %.3e)" % (
-                           2.0 * (w["V"] / world * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * w["k"] + 16)),
-                       "kernel": "scan_tc_kernel (per GPU; step time includes the row-norm and merge kernels)"}
+    traffic, traffic_src = ncu_traffic(args.workload, world, "panel_scan" if w["Q"] <= 128 else "scan_tc")
+    alg_bytes = 2.0 * (w["V"] / world * w["D"] + w["Q"] * w["D"]) + w["Q"] * (8 * w["k"] + 16)
+    if w["Q"] <= 128:
+        # one row block: AI ~ Q flop/B, the table read bounds the scan (panel_scan.cu, ONE launch per step);
+        # `achieved` from the direct-call step time, `graphed` from CUDA-graph replays of the same step
+        gbs = alg_bytes / (res["ms_per_step"] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": gbs / pk["hbm_gbs"], "peak_source": pk["source"] + " (burst copy)",
+                           "traffic": traffic, "traffic_source": traffic_src,
+                           "traffic_unit": "bytes per launch (algorithmic: %.3e)" % alg_bytes,
+                           "kernel": "panel_scan_kernel (per GPU; the step is this one launch)"}
+        if "graphed_ms_per_step" in res:
+            gg = alg_bytes / (res["graphed_ms_per_step"] * 1e-3) / 1e9
+            out["roofline"]["graphed"] = {"ms_per_step": res["graphed_ms_per_step"], "achieved": gg, "frac": gg / pk["hbm_gbs"]}
+        if "cold_ms_per_step" in res:
+            cg = alg_bytes / (res["cold_ms_per_step"] * 1e-3) / 1e9
+            out["roofline"]["cold_l2"] = {"ms_per_step": res["cold_ms_per_step"], "achieved": cg, "frac": cg / pk["hbm_gbs"]}
+    else:
+        out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                           "frac": achieved / pk["bf16_tflops"], "frac_of_sustained": achieved / pk["bf16_tflops_sustained"],
+                           "peak_source": pk["source"] + " (burst cuBLAS bf16)",
+                           # dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel, one launch of this
+                           # workload, read from the committed ncu --set full raw page named in traffic_source
+                           "traffic": traffic, "traffic_source": traffic_src,
+                           "traffic_unit": "bytes per launch (algorithmic: %.3e)" % alg_bytes,
+                           "kernel": "scan_tc_kernel (per GPU; step time includes the row-norm and merge kernels)"}
     out["drift_wait_timeouts"] = int(mcl.set_option(103, 0))
     if world == 1 and rank == 0 and not args.profile:
         q, table, labels = res["inputs"]
@@ -687,7 +709,7 @@ def main():
         cpu_reference_step.__dict__.get("tables", {}).clear()
         if not args.no_sweep:
             sweep = []
-            for name in ("c1", "c2", "gemma3_head", "c4", "c5"):
+            for name in ("c1", "c2", "gemma3_head", "gemma3_eval", "c4", "c5"):
                 if name == args.workload:
                     continue
                 try:

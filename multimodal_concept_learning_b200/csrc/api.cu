@@ -107,8 +107,9 @@ ScanLayout scan_layout(int64_t Q, int64_t V, int64_t D, int k, int dtype, int sm
     const int num_vt = (int)((V + kBlockN - 1) / kBlockN), num_kb = (int)((D + kBlockK - 1) / kBlockK);
     L.small_ld = (V + kChunk - 1) / kChunk * kChunk;
     L.scores_bytes = (((size_t)Q * L.small_ld * sizeof(float)) + 255) & ~(size_t)255;
-    // (k = 1 needs no score dump: the running argmax of the top-1 epilogue is the answer)
-    L.small = num_rb == 1 && L.mode == 0 && L.scores_bytes <= kSmallScoreBytesMax && !g_opt_nosmall.load();
+    // (the two-kernel path is built on the top-k epilogue mode; k = 1 reaches the one-launch path only)
+    L.small = num_rb == 1 && (L.mode == 0 || !g_opt_nopanel.load()) && L.scores_bytes <= kSmallScoreBytesMax &&
+              !g_opt_nosmall.load();
     // Seeding pays where the epilogue, not the tensor pipe, bounds the scan (D <= 1536) and the
     // sample -- ~2.5 k chunk maxima per row, at most 16 tiles -- is under a tenth of the table.
     const int nt = std::min(16, (5 * k / 2 + 7) / 8);

@@ -173,6 +173,11 @@ __device__ __forceinline__ void pn_select_row(const PnParams& p, PnScratch& sc, 
   const bool few = ng <= 4 * kPnThreads;
   float4 pv = make_float4(-INFINITY, 0.f, 0.f, 0.f);
   if (tid < G) pv = __ldcg(p.part + (size_t)tid * p.Q + row);
+  float zl = 0.f;                                 // the label's score (thread 0)
+  if (tid == 0 && p.labels) {
+    const long long lg = p.labels[row], l = lg - p.index_base;
+    if (lg != -100 && l >= 0 && l < n) zl = __ldcg(src + l);
+  }
   uint32_t gkey[4] = {0u, 0u, 0u, 0u};            // keys of finite scores are never 0
   uint32_t mx = 0u;
   if (few) {
@@ -227,11 +232,6 @@ __device__ __forceinline__ void pn_select_row(const PnParams& p, PnScratch& sc, 
     float m = -INFINITY, s = 0.f, sz = 0.f;
 #pragma unroll
     for (int w = 0; w < kPnWarps; ++w) { lse_fold(m, s, sc.red[w][0], sc.red[w][1]); sz += sc.red[w][2]; }
-    float zl = 0.f;
-    if (p.labels) {
-      const long long lg = p.labels[row], l = lg - p.index_base;
-      if (lg != -100 && l >= 0 && l < n) zl = __ldcg(src + l);
-    }
     p.row_stats[row] = make_float4(m, s, sz, zl);
   }
   // groups whose maximum reaches the bound (block-uniform trip counts: warp collectives inside)
@@ -364,8 +364,8 @@ __device__ __forceinline__ void pn_select_row(const PnParams& p, PnScratch& sc, 
 
 template <int NQ>
 __global__ void __launch_bounds__(kPnThreads, 1)
-panel_scan_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_q,
-                  const PnParams p) {
+panel_scan_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_t32,
+                  const __grid_constant__ CUtensorMap tm_q, const PnParams p) {
   constexpr uint32_t kQBytes = NQ * kBlockK * 2;                 // 2 .. 16 KB
   constexpr uint32_t kStageBytes = kPnTBytes + kQBytes;
   constexpr uint32_t kStages = kPnRingBytes / kStageBytes;       // 10 (NQ = 16) .. 6 (NQ = 128)
@@ -401,6 +401,7 @@ panel_scan_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constan
   stamp(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_t);
+    tma_prefetch_desc(&tm_t32);
     tma_prefetch_desc(&tm_q);
   }
   if (warp == 1) {
@@ -419,30 +420,44 @@ panel_scan_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int G = (int)gridDim.x;
-  const int t0 = (int)((long long)blockIdx.x * p.num_tiles / G);
-  const int t1 = (int)((long long)(blockIdx.x + 1) * p.num_tiles / G);
+  // This CTA's table rows: a contiguous range of whole groups of 32 rows (the unit of the group
+  // maxima), walked in panels of 128; the last panel may be short -- only its rows are fetched
+  // (32-row TMA boxes), the MMA runs over the stale rest of the stage and nobody reads those lanes.
+  const int ngroups = (p.V + 31) >> 5;
+  const int r0 = (int)((long long)blockIdx.x * ngroups / G) * 32;
+  const int r1 = min(p.V, (int)((long long)(blockIdx.x + 1) * ngroups / G) * 32);
+  const int npanel = (r1 - r0 + kPnM - 1) / kPnM;
   const int num_kb = p.num_kb;
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = t0; t < t1; ++t)
+      for (int t = 0; t < npanel; ++t) {
+        const int row = r0 + t * kPnM;
+        const int nbox = min(4, (r1 - row + 31) >> 5);          // 32-row boxes of this panel
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_backoff(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          mbar_expect_tx(full_bar(stage), kStageBytes);
-          tma_load_2d(sa, &tm_t, full_bar(stage), kb * kBlockK, t * kPnM, kL2EvictNormal);
+          if (nbox == 4) {
+            mbar_expect_tx(full_bar(stage), kStageBytes);
+            tma_load_2d(sa, &tm_t, full_bar(stage), kb * kBlockK, row, kL2EvictNormal);
+          } else {
+            mbar_expect_tx(full_bar(stage), kQBytes + nbox * 4096u);
+            for (int b = 0; b < nbox; ++b)                       // 32 rows x 128 B = four swizzle atoms
+              tma_load_2d(sa + b * 4096u, &tm_t32, full_bar(stage), kb * kBlockK, row + 32 * b, kL2EvictNormal);
+          }
           tma_load_2d(sa + kPnTBytes, &tm_q, full_bar(stage), kb * kBlockK, 0, kL2EvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+      }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kPnM, NQ);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int t = t0; t < t1; ++t) {
+      for (int t = 0; t < npanel; ++t) {
         mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u);      // the epilogue has drained this stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * NQ;
@@ -494,16 +509,17 @@ panel_scan_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constan
 #pragma unroll
       for (int j = 0; j < NQ / 16; ++j) { run_m[j] = -INFINITY; run_s[j] = 0.f; run_z[j] = 0.f; }
       uint32_t acc = 0, acc_phase = 0;
-      for (int t = t0; t < t1; ++t) {
-        const int row = t * kPnM + quarter * 32 + lane;  // table row of this thread
-        const bool rv = row < p.V;
-        const bool warp_rows = t * kPnM + quarter * 32 < p.V;   // (uniform) the warp holds table rows
+      for (int t = 0; t < npanel; ++t) {
+        const int wrow = r0 + t * kPnM + quarter * 32;   // first table row of this warp (a whole group)
+        const int row = wrow + lane;                     // table row of this thread
+        const bool rv = row < r1;
+        const bool warp_rows = wrow < r1;                // (uniform) the warp holds table rows
         const float it = (p.inv_t && rv) ? __ldg(p.inv_t + row) : 1.f;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NQ;
         float* dst = p.scores + row;
-        uint32_t* gdst = p.gmax + (size_t)(t * 4 + quarter);
+        uint32_t* gdst = p.gmax + (size_t)(wrow >> 5);
 #pragma unroll
         for (int j = 0; j < NQ / 16; ++j) {
           if (j % kEG != eg) continue;                   // (uniform)
@@ -633,7 +649,8 @@ std::atomic<unsigned> g_pn_next{0};
 std::mutex g_pn_mu;
 
 template <int NQ>
-cudaError_t pn_launch(int grid, cudaStream_t s, const CUtensorMap& tm_t, const CUtensorMap& tm_q, const PnParams& p) {
+cudaError_t pn_launch(int grid, cudaStream_t s, const CUtensorMap& tm_t, const CUtensorMap& tm_t32, const CUtensorMap& tm_q,
+                      const PnParams& p) {
   static std::atomic<bool> attr_set[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -642,7 +659,7 @@ cudaError_t pn_launch(int grid, cudaStream_t s, const CUtensorMap& tm_t, const C
     if (e != cudaSuccess) return e;
     attr_set[dev].store(true);
   }
-  panel_scan_kernel<NQ><<<grid, kPnThreads, kPnSmemBytes, s>>>(tm_t, tm_q, p);
+  panel_scan_kernel<NQ><<<grid, kPnThreads, kPnSmemBytes, s>>>(tm_t, tm_t32, tm_q, p);
   return cudaGetLastError();
 }
 }  // namespace
@@ -680,8 +697,9 @@ cudaError_t launch_panel_scan(const ScanArgs& a, int sm_count, float* scores, in
     }
   }
   const int NQ = a.Q <= 16 ? 16 : (a.Q <= 32 ? 32 : (a.Q <= 64 ? 64 : 128));
-  CUtensorMap tm_t, tm_q;
-  if (!make_tmap_bf16(&tm_t, a.table, a.V, a.D, a.ldt, kPnM) || !make_tmap_bf16(&tm_q, a.q, a.Q, a.D, a.ldq, NQ)) {
+  CUtensorMap tm_t, tm_t32, tm_q;
+  if (!make_tmap_bf16(&tm_t, a.table, a.V, a.D, a.ldt, kPnM) || !make_tmap_bf16(&tm_t32, a.table, a.V, a.D, a.ldt, 32) ||
+      !make_tmap_bf16(&tm_q, a.q, a.Q, a.D, a.ldq, NQ)) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (Q=%lld V=%lld D=%lld ldq=%lld ldt=%lld)",
              (long long)a.Q, (long long)a.V, (long long)a.D, (long long)a.ldq, (long long)a.ldt);
     return cudaErrorInvalidValue;
@@ -700,12 +718,12 @@ cudaError_t launch_panel_scan(const ScanArgs& a, int sm_count, float* scores, in
   p.sync = g_pn_sync[dev] + 16 * (g_pn_next.fetch_add(1) % 64);
   p.fault = g_pn_fault[dev];
   p.timing = (unsigned long long*)a.timing;
-  const int grid = std::min(sm_count, p.num_tiles);
+  const int grid = std::min(sm_count, (int)((a.V + 31) / 32));   // every CTA owns at least one group of 32 rows
   switch (NQ) {
-    case 16: return pn_launch<16>(grid, s, tm_t, tm_q, p);
-    case 32: return pn_launch<32>(grid, s, tm_t, tm_q, p);
-    case 64: return pn_launch<64>(grid, s, tm_t, tm_q, p);
-    default: return pn_launch<128>(grid, s, tm_t, tm_q, p);
+    case 16: return pn_launch<16>(grid, s, tm_t, tm_t32, tm_q, p);
+    case 32: return pn_launch<32>(grid, s, tm_t, tm_t32, tm_q, p);
+    case 64: return pn_launch<64>(grid, s, tm_t, tm_t32, tm_q, p);
+    default: return pn_launch<128>(grid, s, tm_t, tm_t32, tm_q, p);
   }
 }
 

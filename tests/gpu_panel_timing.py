@@ -68,7 +68,7 @@ for (Q, V, D, k) in [(16, 50257, 768, 50), (96, 50257, 768, 50), (16, 262235, 11
     stats = torch.empty((Q, 4), dtype=torch.float32, device="cuda")
     wsb = lib.mcl_scan_workspace_bytes(Q, V, D, k, 0)
     ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
-    grid = min(148, (V + 127) // 128)
+    grid = min(148, (V + 31) // 32)
     mcl.set_option(3, 1)
     for rep in range(4):
         rc = lib.mcl_concept_scan(q.data_ptr(), t.data_ptr(), 0, Q, V, D, D, D, iq.data_ptr(), it.data_ptr(), 1.0, k, 0, None,

@@ -554,6 +554,14 @@ def test_top1_epilogue_equals_general_path_and_oracle(mcl, Q, V, D, cap):
     finally:
         mcl.set_option(14, old)
     assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+    if Q <= 128:                                      # one row block: `a` took the one-launch panel path;
+        old = mcl.set_option(18, 1)                   # option 18 sends k = 1 through the running-argmax epilogue
+        try:
+            c = mcl.concept_scan(qd, td, 1, **kw)
+        finally:
+            mcl.set_option(18, old)
+        assert torch.equal(a.topk_idx, c.topk_idx) and torch.equal(a.topk_val, c.topk_val)
+        torch.testing.assert_close(a.stats, c.stats, rtol=1e-5, atol=1e-3)
     # (sums in a different order of addition: one-row-block batches take the panel path under option 14)
     torch.testing.assert_close(a.stats[:, [0, 3]], b.stats[:, [0, 3]], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(a.stats, b.stats, rtol=1e-5, atol=1e-3)
