@@ -101,6 +101,40 @@ def test_gather_mean(mcl, dtype, normalize):
         assert torch.equal(got[i], table[sel].mean(dim=0))
 
 
+@pytest.mark.parametrize("dtype,V,D,Q,maxlen", [(torch.bfloat16, 9000, 3584, 2000, 5), (torch.float32, 4000, 2048, 3000, 13), (torch.bfloat16, 3000, 768, 5000, 3),
+                                                (torch.bfloat16, 700, 4096, 37, 70), (torch.float32, 2000, 1024, 900, 6),
+                                                (torch.bfloat16, 500, 72, 3000, 4), (torch.bfloat16, 500, 100, 300, 4),
+                                                (torch.float32, 300, 2052, 100, 40), (torch.bfloat16, 64, 8, 1, 1)])
+def test_gather_mean_bulk_copy_rings_equal_register_kernels(mcl, dtype, V, D, Q, maxlen):
+    """The default gather (per-warp rings of cp.async.bulk row copies) against the register
+    kernels (library option 17) and the oracle: bit-identical, on rows longer than a 32-id chunk,
+    empty rows, warps without rows (Q < warps), row sizes that are not 16-byte multiples (D = 100
+    bf16: both settings take the register path) and fp32 tables."""
+    g = torch.Generator().manual_seed(V + D)
+    table = torch.randn(V, D, generator=g).to(dtype)
+    lens = torch.randint(0, maxlen + 1, (Q,), generator=g)
+    if Q > 3:
+        lens[1] = 0
+        lens[Q - 1] = 0
+    offs = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
+    ids = torch.randint(0, V, (int(offs[-1]),), generator=g)
+    td = table.cuda()
+    for normalize in (False, True):
+        a = mcl.gather_mean(td, offs, ids, normalize)
+        old = mcl.set_option(17, 1)
+        try:
+            b = mcl.gather_mean(td, offs, ids, normalize)
+        finally:
+            mcl.set_option(17, old)
+        assert torch.equal(a, b)
+        want = R.gather_mean_ref(table, offs.tolist(), ids, normalize=normalize)
+        if dtype == torch.bfloat16 and not normalize:
+            assert torch.equal(a.cpu(), want)
+        else:
+            torch.testing.assert_close(a.cpu().float(), want.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-6,
+                                       atol=1e-6)
+
+
 def test_gather_mean_empty_and_single(mcl):
     table = torch.arange(40, dtype=torch.float32).reshape(5, 8).to(torch.bfloat16).cuda()
     out = mcl.gather_mean(table, torch.tensor([0, 0, 1]), torch.tensor([3]))
