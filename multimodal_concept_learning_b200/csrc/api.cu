@@ -11,7 +11,7 @@
 #include "kernels.h"
 
 using namespace mcl;
-namespace mcl { extern std::atomic<int> g_gather_variant; }
+namespace mcl { extern std::atomic<int> g_gather_variant, g_merge_variant; }
 
 namespace {
 
@@ -886,6 +886,7 @@ int64_t mcl_set_option(int opt, int64_t value) {
   if (opt == 16) return g_opt_noqnorm.exchange(value);
   if (opt == 17) return g_gather_variant.exchange((int)value);
   if (opt == 18) return g_opt_nopanel.exchange(value);
+  if (opt == 19) return g_merge_variant.exchange((int)value);
   if (opt == 103) return drift_timeouts_total();
   if (opt == 104) return panel_barrier_faults();
   if (opt >= 100 && opt < 103) return (int64_t)(g_phase_ms[opt - 100] * 1.0e6f);   // read-back, ns

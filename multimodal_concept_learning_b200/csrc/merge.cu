@@ -10,6 +10,8 @@
 
 namespace mcl {
 
+std::atomic<int> g_merge_variant{0};   // library option 19: 1 = the streaming-fold merge kernels only (A/B)
+
 // kWPR warps per query row (1 for the usual handful of slots, 16 when a small Q was split over
 // all SMs).  Phase A: the largest threshold any slot recorded for the row is a lower bound of
 // its global k-th best, so only candidates at or above it can matter -- typically ~2k of the
@@ -37,23 +39,42 @@ merge_slots_kernel(SlotView sv, const SlotMap map, int Q, int k, const float* __
   const unsigned lt = (1u << lane) - 1u;
 
   // ---- phase A: bound, and (warp 0 of the row) the merged statistics ---------------------
-  uint32_t bound = 0u;
-  if (live)
+  // Rows with at most 32 slots (every multi-row-block plan): lane i holds slot i's count, threshold
+  // and statistics -- ONE round trip -- and phase B below fetches the candidate lists of two slots
+  // at a time with all their loads in flight.  (A warp used to walk count -> 32 entries -> next 32
+  // entries ... slot after slot: ~18 dependent L2 round trips per row, which made this kernel
+  // 100 us at 8192 rows x 10 slots -- 12 % of an eight-way shard's step.)
+  const bool few = nsplit <= 32;
+  int2 c_l = make_int2(0, 0);
+  float4 st_l = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+  if (live && few && lane < nsplit) {
+    c_l = __ldcg(&sv.cnt[(size_t)(slot0 + lane) * kBlockM + r_in]);
+    if (wr == 0) st_l = __ldcg(&sv.stats[(size_t)(slot0 + lane) * kBlockM + r_in]);
+  }
+  uint32_t bound = (uint32_t)c_l.y;
+  if (live && !few)
     for (int i = lane; i < nsplit; i += 32)
       bound = max(bound, (uint32_t)sv.cnt[(size_t)(slot0 + i) * kBlockM + r_in].y);
   bound = __reduce_max_sync(0xffffffffu, bound);
   if (live && wr == 0) {
-    float m = -INFINITY;
-    for (int i = lane; i < nsplit; i += 32)
-      m = fmaxf(m, sv.stats[(size_t)(slot0 + i) * kBlockM + r_in].x);
+    float m = st_l.x;
+    if (!few)
+      for (int i = lane; i < nsplit; i += 32)
+        m = fmaxf(m, sv.stats[(size_t)(slot0 + i) * kBlockM + r_in].x);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     float s = 0.f, sum_z = 0.f, z_label = 0.f;
-    for (int i = lane; i < nsplit; i += 32) {
-      const float4 st = sv.stats[(size_t)(slot0 + i) * kBlockM + r_in];
-      s += (st.y > 0.f) ? st.y * expf(st.x - m) : 0.f;
-      sum_z += st.z;
-      z_label += st.w;
+    if (few) {
+      s = (st_l.y > 0.f) ? st_l.y * expf(st_l.x - m) : 0.f;
+      sum_z = st_l.z;
+      z_label = st_l.w;
+    } else {
+      for (int i = lane; i < nsplit; i += 32) {
+        const float4 st = sv.stats[(size_t)(slot0 + i) * kBlockM + r_in];
+        s += (st.y > 0.f) ? st.y * expf(st.x - m) : 0.f;
+        sum_z += st.z;
+        z_label += st.w;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -81,39 +102,64 @@ merge_slots_kernel(SlotView sv, const SlotMap map, int Q, int k, const float* __
     const int p = k - 1;
     kth = shfl64(p < 32 ? top.r0 : top.r1, p & 31);
   };
-  if (live) {
+  auto consume = [&](const uint2 e, bool valid) {        // (all 32 lanes call)
+    unsigned long long key = 0ull;
+    if (valid && f2key(__uint_as_float(e.x)) >= bound) {  // can still be among the row's k best
+      // rank by the OUTPUT value z (what callers and the rank merge see), so that scores
+      // whose z round to the same float tie-break by table row everywhere
+      float z = __uint_as_float(e.x) * rs;
+      if (softcap > 0.f) z = softcap * tanhf(z / softcap);
+      key = pack_key(z, e.y);
+    }
+    const bool keep = key > kth;          // keys are unique, so > loses nothing
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) q[npend + __popc(km & lt)] = key;
+    npend += __popc(km);
+    __syncwarp();
+    if (npend >= 64) flush64();
+  };
+  if (live && few) {
+    constexpr int kT = kCandCap / 32;     // loads per lane and slot
+    for (int i = wr; i < nsplit; i += 2 * kWPR) {         // (warp-uniform)
+      const int i1 = i + kWPR;
+      const int n0 = __shfl_sync(0xffffffffu, c_l.x, i);
+      const int n1 = __shfl_sync(0xffffffffu, c_l.x, i1 & 31);
+      const bool two = i1 < nsplit;
+      const uint2* b0 = sv.cand + ((size_t)(slot0 + i) * kBlockM + r_in) * kCandCap;
+      const uint2* b1 = sv.cand + ((size_t)(slot0 + (two ? i1 : i)) * kBlockM + r_in) * kCandCap;
+      uint2 e0[kT], e1[kT];
+#pragma unroll
+      for (int t = 0; t < kT; ++t) {
+        const int j = 32 * t + lane;
+        e0[t] = (j < n0) ? __ldcg(b0 + j) : make_uint2(0u, 0u);
+        e1[t] = (two && j < n1) ? __ldcg(b1 + j) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int t = 0; t < kT; ++t)
+        if (32 * t < n0) consume(e0[t], 32 * t + lane < n0);
+      if (two) {
+#pragma unroll
+        for (int t = 0; t < kT; ++t)
+          if (32 * t < n1) consume(e1[t], 32 * t + lane < n1);
+      }
+    }
+  } else if (live) {
     for (int i = wr; i < nsplit; i += kWPR) {
       const int slot = slot0 + i;
       const int n = sv.cnt[(size_t)slot * kBlockM + r_in].x;
       const uint2* b = sv.cand + ((size_t)slot * kBlockM + r_in) * kCandCap;
       for (int base = 0; base < n; base += 32) {
         const int j = base + lane;
-        unsigned long long key = 0ull;
-        if (j < n) {
-          const uint2 e = b[j];
-          if (f2key(__uint_as_float(e.x)) >= bound) {   // can still be among the row's k best
-            // rank by the OUTPUT value z (what callers and the rank merge see), so that scores
-            // whose z round to the same float tie-break by table row everywhere
-            float z = __uint_as_float(e.x) * rs;
-            if (softcap > 0.f) z = softcap * tanhf(z / softcap);
-            key = pack_key(z, e.y);
-          }
-        }
-        const bool keep = key > kth;      // keys are unique, so > loses nothing
-        const unsigned km = __ballot_sync(0xffffffffu, keep);
-        if (keep) q[npend + __popc(km & lt)] = key;
-        npend += __popc(km);
-        __syncwarp();
-        if (npend >= 64) flush64();
+        consume(j < n ? b[j] : make_uint2(0u, 0u), j < n);
       }
     }
-    if (npend > 0) {                      // tail: pad the queue to 64 with empty keys
-      if (lane + npend < 64) q[npend + lane] = 0ull;
-      if (lane + npend + 32 < 64) q[npend + 32 + lane] = 0ull;
-      __syncwarp();
-      npend = 64;
-      flush64();
-    }
+  }
+  if (live && npend > 0) {                // tail: pad the queue to 64 with empty keys
+    if (lane + npend < 64) q[npend + lane] = 0ull;
+    if (lane + npend + 32 < 64) q[npend + 32 + lane] = 0ull;
+    __syncwarp();
+    npend = 64;
+    flush64();
   }
   // ---- phase C ----------------------------------------------------------------------------
   if (kWPR > 1) {
@@ -133,6 +179,207 @@ merge_slots_kernel(SlotView sv, const SlotMap map, int Q, int k, const float* __
       topk_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32));
       topk_idx[(size_t)row * k + p] =
           empty ? -1ll : index_base + (long long)(uint32_t)(~(uint32_t)key);
+    }
+  }
+}
+
+// One warp per row, selection before sorting (rows with at most 32 slots, launches with enough
+// rows to fill the chip).  ncu on the kernel above at 8192 rows x 10 slots
+// (profiles/r02_merge_slots_c3_8_ncu_raw.csv): 61 % issue utilisation, 7 k warp instructions per
+// row, 70 % of them ISETP / SEL / SHFL of the bitonic networks -- the slots' own thresholds pass
+// ~4k candidates per row, which cost four or five 64-key sorts.  Here:
+//   1. lane i reads slot i's count, threshold and statistics (one round trip); the candidate lists
+//      are fetched two slots at a time with all loads in flight; entries at or above the largest
+//      slot threshold (a lower bound of the row's k-th best) become 64-bit keys in shared memory;
+//   2. with more than 64 of them a pivot p with k <= #{key >= p} <= 64 is searched with warp-wide
+//      counts (16 keys per lane in registers, ~50 instructions per count): the first pivots
+//      interpolate on the logarithm of the counts -- score tails are close to exponential --, then
+//      plain bisection of the 64-bit key interval, which always ends because keys are unique;
+//   3. ONE 64-key sort of the keys >= p.
+// More than 512 keys above the bound (adversarial thresholds): the streaming fold of the kernel
+// above.  Same keys, same order: bit-identical outputs (tests/test_gpu_parity.py compare the
+// kernels through library option 19).
+constexpr int kSurvCap = 512;
+
+__global__ void __launch_bounds__(128)
+merge_rows_kernel(SlotView sv, const SlotMap map, int Q, int k, const float* __restrict__ inv_q,
+                  float scale, float softcap, long long index_base, float* __restrict__ topk_val,
+                  long long* __restrict__ topk_idx, float4* __restrict__ row_stats) {
+  __shared__ unsigned long long surv[4][kSurvCap];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= Q) return;                                   // (no block-wide barrier below)
+  const int rb = row / kBlockM, r_in = row % kBlockM;
+  const int slot0 = rb * map.stride;
+  const int nsplit = slotmap_count(map, rb);              // <= 32 (the launcher checks the stride)
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned long long* sq = surv[warp];
+
+  int2 c_l = make_int2(0, 0);
+  float4 st_l = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+  if (lane < nsplit) {
+    c_l = __ldcg(&sv.cnt[(size_t)(slot0 + lane) * kBlockM + r_in]);
+    st_l = __ldcg(&sv.stats[(size_t)(slot0 + lane) * kBlockM + r_in]);
+  }
+  const float rs = (inv_q ? inv_q[row] : 1.f) * scale;
+  const uint32_t bound = __reduce_max_sync(0xffffffffu, (uint32_t)c_l.y);
+  {
+    float m = st_l.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = (st_l.y > 0.f) ? st_l.y * expf(st_l.x - m) : 0.f, sum_z = st_l.z, z_label = st_l.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      sum_z += __shfl_xor_sync(0xffffffffu, sum_z, o);
+      z_label += __shfl_xor_sync(0xffffffffu, z_label, o);
+    }
+    if (lane == 0) row_stats[row] = make_float4(m, s, sum_z, z_label);
+  }
+
+  // ---- 1. candidates at or above the bound -> keys in shared memory --------------------------
+  int ns = 0;                                             // (warp-uniform)
+  auto keep_key = [&](const uint2 e, bool valid) {
+    unsigned long long key = 0ull;
+    if (valid && f2key(__uint_as_float(e.x)) >= bound) {
+      float z = __uint_as_float(e.x) * rs;                // rank by the OUTPUT value (see above)
+      if (softcap > 0.f) z = softcap * tanhf(z / softcap);
+      key = pack_key(z, e.y);
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, key != 0ull);
+    const int pos = ns + __popc(km & lt);
+    if (key != 0ull && pos < kSurvCap) sq[pos] = key;
+    ns += __popc(km);
+  };
+  constexpr int kT = kCandCap / 32;                       // loads per lane and slot
+  for (int i = 0; i < nsplit; i += 2) {
+    const int n0 = __shfl_sync(0xffffffffu, c_l.x, i);
+    const int n1 = __shfl_sync(0xffffffffu, c_l.x, (i + 1) & 31);
+    const bool two = i + 1 < nsplit;
+    const uint2* b0 = sv.cand + ((size_t)(slot0 + i) * kBlockM + r_in) * kCandCap;
+    const uint2* b1 = b0 + (two ? (size_t)kBlockM * kCandCap : 0);
+    uint2 e0[kT], e1[kT];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) {
+      const int j = 32 * t + lane;
+      e0[t] = (j < n0) ? __ldcg(b0 + j) : make_uint2(0u, 0u);
+      e1[t] = (two && j < n1) ? __ldcg(b1 + j) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int t = 0; t < kT; ++t)
+      if (32 * t < n0) keep_key(e0[t], 32 * t + lane < n0);
+    if (two) {
+#pragma unroll
+      for (int t = 0; t < kT; ++t)
+        if (32 * t < n1) keep_key(e1[t], 32 * t + lane < n1);
+    }
+  }
+  __syncwarp();
+
+  TopList top; top.init();
+  if (ns > kSurvCap) {
+    // ---- too many keys above the bound: streaming fold (the algorithm of merge_slots_kernel)
+    unsigned long long kth = 0ull;
+    int npend = 0;
+    auto flush64 = [&]() {
+      const unsigned long long b0 = sq[lane], b1 = sq[32 + lane];
+      const unsigned long long rest = (64 + lane < npend) ? sq[64 + lane] : 0ull;
+      __syncwarp();
+      top.push(b0, b1, lane);
+      npend -= 64;
+      if (lane < npend) sq[lane] = rest;
+      __syncwarp();
+      const int p = k - 1;
+      kth = shfl64(p < 32 ? top.r0 : top.r1, p & 31);
+    };
+    for (int i = 0; i < nsplit; ++i) {
+      const int n = __shfl_sync(0xffffffffu, c_l.x, i);
+      const uint2* b = sv.cand + ((size_t)(slot0 + i) * kBlockM + r_in) * kCandCap;
+      for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        unsigned long long key = 0ull;
+        if (j < n) {
+          const uint2 e = __ldcg(b + j);
+          if (f2key(__uint_as_float(e.x)) >= bound) {
+            float z = __uint_as_float(e.x) * rs;
+            if (softcap > 0.f) z = softcap * tanhf(z / softcap);
+            key = pack_key(z, e.y);
+          }
+        }
+        const bool keep = key > kth;
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) sq[npend + __popc(km & lt)] = key;
+        npend += __popc(km);
+        __syncwarp();
+        if (npend >= 64) flush64();
+      }
+    }
+    if (npend > 0) {
+      if (lane + npend < 64) sq[npend + lane] = 0ull;
+      if (lane + npend + 32 < 64) sq[npend + 32 + lane] = 0ull;
+      __syncwarp();
+      npend = 64;
+      flush64();
+    }
+  } else {
+    // ---- 2. a pivot with k <= #{key >= pivot} <= 64 ---------------------------------------------
+    unsigned long long kr[kSurvCap / 32];
+#pragma unroll
+    for (int i = 0; i < kSurvCap / 32; ++i) kr[i] = (32 * i + lane < ns) ? sq[32 * i + lane] : 0ull;
+    unsigned long long pivot = 1ull;                       // every key (keys are never 0)
+    if (ns > 64) {
+      unsigned long long mx = 0ull, mn = ~0ull;
+#pragma unroll
+      for (int i = 0; i < kSurvCap / 32; ++i) { mx = max64(mx, kr[i]); if (kr[i]) mn = min64(mn, kr[i]); }
+      const uint32_t hi_w = __reduce_max_sync(0xffffffffu, (uint32_t)(mx >> 32));
+      const uint32_t lo_w = __reduce_min_sync(0xffffffffu, (uint32_t)(mn >> 32));
+      unsigned long long lo = (unsigned long long)lo_w << 32;          // #{>= lo} = ns   (> 64)
+      unsigned long long hi = hi_w == 0xffffffffu ? ~0ull : ((unsigned long long)hi_w + 1ull) << 32;   // #{>= hi} = 0 (< k)
+      float c_lo = (float)ns, c_hi = 0.5f;
+      for (int it = 0;; ++it) {
+        unsigned long long p;
+        if (it < 6) {                                      // log-linear interpolation, aimed at (k + 64) / 2
+          const float f = (__log2f(c_lo) - __log2f(0.5f * (float)(k + 64))) / (__log2f(c_lo) - __log2f(c_hi));
+          p = lo + (unsigned long long)((double)(hi - lo) * (double)fminf(fmaxf(f, 0.02f), 0.98f));
+        } else {
+          p = lo + ((hi - lo) >> 1);
+        }
+        if (p <= lo) p = lo + 1ull;                        // (hi - lo >= 2 while the search runs: see below)
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < kSurvCap / 32; ++i) c += (kr[i] >= p) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c > 64) { lo = p; c_lo = (float)c; }
+        else if (c < k) { hi = p; c_hi = fmaxf((float)c, 0.5f); }
+        else { pivot = p; break; }
+        // keys are unique: #{>= lo} > 64 and #{>= hi} < k put more than 64 - k + 1 >= 1 keys inside
+        // [lo, hi), so the interval cannot shrink below two values before a pivot is found
+      }
+    }
+    // ---- 3. one sort of the keys at or above the pivot ------------------------------------------
+    int nk = 0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kSurvCap / 32; ++i) {
+      if (32 * i < ns) {                                   // (uniform)
+        const bool keep = kr[i] >= pivot && kr[i] != 0ull;
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) sq[nk + __popc(km & lt)] = kr[i];        // nk <= 64: positions below the sources read above
+        nk += __popc(km);
+      }
+    }
+    __syncwarp();
+    const unsigned long long b0 = lane < nk ? sq[lane] : 0ull, b1 = 32 + lane < nk ? sq[32 + lane] : 0ull;
+    top.push(b0, b1, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int p = i * 32 + lane;
+    const uint64_t key = i ? top.r1 : top.r0;
+    if (p < k) {
+      const bool empty = (key == 0ull);
+      topk_val[(size_t)row * k + p] = empty ? -INFINITY : key2f((uint32_t)(key >> 32));
+      topk_idx[(size_t)row * k + p] = empty ? -1ll : index_base + (long long)(uint32_t)(~(uint32_t)key);
     }
   }
 }
@@ -285,18 +532,24 @@ cudaError_t launch_merge_slots(const SlotView& sv, const SlotMap& map, int64_t Q
                          cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(merge_slots_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(merge_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(merge_ranks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     pref_set[dev].store(true);
   }
+  // enough rows to fill the chip with one warp each, at most 32 slots per row: select, then sort once
+  if (map.stride <= 32 && Q >= 2048 && !g_merge_variant.load())
+    merge_rows_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, s>>>(
+        sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
+        (float4*)row_stats);
   // few rows with many slots (small Q split over all SMs): more warps per row
-  if (map.stride > 32 && Q <= 4096)
+  else if (map.stride > 32 && Q <= 4096)
     merge_slots_kernel<16><<<(unsigned)Q, 32 * 16, 0, s>>>(
         sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,
         (float4*)row_stats);
-  // A warp walks its slots one after the other (count -> entries -> sort: a dependent chain of L2
-  // round trips per slot), so rows with 8+ slots are split over four warps while the launch still
-  // fits the chip in a wave or two
+  // A warp walks its slots one after the other, so rows with 8+ slots are split over four warps
+  // while the launch still fits the chip in a wave or two
   else if (map.stride >= 8 && Q <= 16384)
     merge_slots_kernel<4><<<(unsigned)Q, 128, 0, s>>>(
         sv, map, (int)Q, k, inv_q, scale, softcap, (long long)index_base, topk_val, (long long*)topk_idx,

@@ -538,6 +538,41 @@ def test_panel_scan_softcap_and_shard_base(mcl, Q, cap):
     check_stats(a.stats, ref, rtol=RTOL, atol=1e-3)
 
 
+@pytest.mark.parametrize("Q,V,D,k,kind", [(2304, 3000, 64, 50, "normal"), (2100, 9000, 128, 64, "normal"),
+                                          (2048, 2600, 72, 7, "dup"), (2304, 3000, 64, 50, "equal"),
+                                          (2200, 5000, 64, 1, "normal")])
+def test_merge_select_then_sort_equals_streaming_fold(mcl, Q, V, D, k, kind):
+    """Launches with >= 2048 rows merge their slots with merge_rows_kernel (bound -> pivot search
+    -> one sort); library option 19 restores the streaming-fold kernel.  Bit-identical outputs, on
+    random scores, on tables with blocks of duplicated rows (ties at the k-th place) and on a table
+    of identical rows (every candidate survives the bound: the kernel's own streaming fallback);
+    and the oracle's answer."""
+    q, t = make_inputs(Q, V, D, 500 + Q + k)
+    if kind == "dup":
+        t[1000:1400] = t[17]                       # 401 equal scores per query: ties decide the top-k
+        t[2000:2300] = t[18]
+    if kind == "equal":
+        t[:] = t[0]
+    labels = torch.randint(0, V, (Q,), generator=torch.Generator().manual_seed(Q))
+    kw = dict(scale=30.0, labels=labels, label_smoothing=0.05)
+    a = mcl.concept_scan(q.cuda(), t.cuda(), k, **kw)
+    old = mcl.set_option(19, 1)
+    try:
+        b = mcl.concept_scan(q.cuda(), t.cuda(), k, **kw)
+    finally:
+        mcl.set_option(19, old)
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_val, b.topk_val)
+    assert torch.equal(a.stats, b.stats)
+    if kind == "equal":
+        assert (a.topk_idx.cpu() == torch.arange(k).expand(Q, k)).all()
+    else:
+        sub = slice(0, 300)
+        ref = R.concept_scan_ref(q[sub], t, k, scale=30.0, labels=labels[sub], label_smoothing=0.05, keep_scores=True)
+        check_topk(a.topk_val[sub], a.topk_idx[sub], ref.scores, k, rtol=RTOL, atol=1e-4)
+        if kind == "dup":                           # exact ties: the lowest rows, in order
+            assert torch.equal(a.topk_idx[sub].cpu(), ref.topk_idx)
+
+
 # ---- edge cases of the domain -----------------------------------------------------------
 def test_empty_query_batch(mcl):
     _, t = make_inputs(1, 500, 64, 80)
