@@ -95,9 +95,12 @@ int mcl_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t 
  * For batches of more than one row block (Q > 128) the [Q x V] score matrix is never written
  * to memory: the top-k filter and the statistics run in the GEMM's epilogue.  Batches of one
  * row block (the reference's 6..96 concept tokens) are bound by the table read, not by the
- * scores: there the epilogue keeps the statistics and drops the Q x V_local scores -- a few
- * percent of the table bytes, L2 resident -- into the workspace, and an exact selection kernel
- * picks the top-k from them (same values, same tie rule; csrc/select.cu).  lse_i = m + log s;
+ * scores: there ONE launch (csrc/panel_scan.cu) streams the table as 128-row UMMA panels, drops
+ * the Q x V_local scores -- a few percent of the table bytes, L2 resident -- into the workspace
+ * with the maxima of every 32 of them, and after an in-kernel grid barrier one CTA per query row
+ * selects the top-k exactly (same values, same tie rule).  The barrier assumes the launch has the
+ * GPU to itself (grid <= SM count); its wait is bounded, and a give-up yields NaN / -1 outputs and
+ * counts in mcl_set_option(104, 0).  lse_i = m + log s;
  * CE_i = (1-eps)(lse_i - z_label) + eps (lse_i - sum_z / V) is formed by the caller.
  * Replaces, in one call:
  *   - sklearn `cosine_similarity` per pair   src/multimodal/token_embedding_analysis.py:237-246
@@ -315,10 +318,15 @@ int mcl_stream_wait_value32(mcl_stream_t stream, const void* dev_addr, uint32_t 
  * k = 1 scans through the general top-k epilogue instead of the running-argmax one (tests, A/B),
  * 15 = what the planner charges a segment's restart in mcl_plan_* (0 = cold top-k filter, 1 = seeded
  * thresholds, 2 = no filter: k = 1 and the seed pass; the scans choose it themselves per call),
- * 16 = 1 keeps the query norms of MCL_SCAN_NORMALIZE_Q out of the scan kernel (tests, A/B);
+ * 16 = 1 keeps the query norms of MCL_SCAN_NORMALIZE_Q out of the scan kernel (tests, A/B),
+ * 17 = 1 runs mcl_gather_mean on the register kernels instead of the bulk-copy rings (A/B),
+ * 18 = 1 sends one-row-block batches through the two-kernel path (scan with the filter off +
+ * selection kernel) instead of the one-launch panel scan (tests, A/B), 19 = 1 merges slots with the
+ * streaming-fold kernels only (tests, A/B of merge_rows_kernel);
  * opt 100..102 read the last memset / scan / merge
  * time in ns; opt 103 reads how many drift waits of the scan kernel timed out (group members
- * that lost L2 locality because a peer CTA was not resident) since the process started.
+ * that lost L2 locality because a peer CTA was not resident) since the process started; opt 104
+ * reads how many grid-barrier waits of the panel scan gave up (its outputs are NaN / -1 then).
  * Returns the old value.
  */
 int64_t mcl_set_option(int opt, int64_t value);
