@@ -195,7 +195,10 @@ def build_step(w, q, table, labels, lo, world, vocab_total):
     import multimodal_concept_learning_b200 as mcl
     if world > 1:
         from multimodal_concept_learning_b200.sharded import ShardedConceptScan
-        sc = ShardedConceptScan(table, vocab_total, normalize_t=w["normalize"])
+        # result exchange: peer-memory stores over NVLink by default ("auto"); MCL_SHARDED_EXCHANGE=nccl
+        # measures the NCCL path (grouped send/recv + all-gather) for comparison
+        sc = ShardedConceptScan(table, vocab_total, normalize_t=w["normalize"],
+                                exchange=os.environ.get("MCL_SHARDED_EXCHANGE", "auto"))
 
         def step(qq=q):
             return sc.scan(qq, w["k"], normalize_q=w["normalize"], scale=w["scale"], labels=labels)
@@ -621,7 +624,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{cfg_name}: {w['desc']}", "Q": w["Q"],
                        "V": w["V"], "D": w["D"], "k": w["k"],
-                       "parallelism": f"vocab-row sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
+                       "parallelism": (f"vocab-row sharding x{args.gpus}, result exchange: "
+                                       + ("NCCL" if os.environ.get("MCL_SHARDED_EXCHANGE") == "nccl" else "peer-memory stores over NVLink")
+                                       ) if args.gpus > 1 else "single GPU",
                        "l2": ("inputs larger than L2 (table {:.2f} GB vs 126 MB)" if w["V"] * w["D"] * 2 > 126e6 else
                               "table {:.2f} GB fits in the 126 MB L2: ms_per_step is warm, roofline.cold_l2 after a 256 MB flush"
                               ).format(w["V"] * w["D"] * 2 / 1e9)}}

@@ -277,6 +277,33 @@ int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtyp
                                 mcl_stream_t stream);
 
 /*
+ * The sharded scan with the result exchange over PEER MEMORY instead of NCCL (csrc/p2p_exchange.cu):
+ * every rank stores each peer's row range of its local lists straight into that peer's block
+ * (one kernel of 16-byte stores over NVLink that ends in a system-scope add on the peer's arrival
+ * counter), the consumer's stream waits for its counter with a stream memory operation, merges its
+ * Q / world rows, and the merged rows travel the same way into every rank's result area.  Two small
+ * kernels and two stream waits replace a grouped ncclSend/ncclRecv and a grouped ncclAllGather.
+ *   peer_blocks[world]  HOST array of device pointers: block r is rank r's (own block at [rank]);
+ *                       each is mcl_sharded_p2p_block_bytes(Q, k, world) bytes from mcl_peer_alloc
+ *                       (zeroed), the others' opened with mcl_peer_open.  One set of blocks serves
+ *                       one (Q, k) shape; `epoch` counts the scans issued on it: 1, 2, 3, ...  (the
+ *                       same on every rank -- the arrival counters are monotone).
+ *   mcl_sharded_p2p_block_bytes returns 0 when the shape cannot take this path (it needs
+ *                       2 <= world <= 16, Q % world == 0 and (Q / world) * k % 4 == 0): use
+ *                       mcl_concept_scan_sharded_ex then.
+ * flags as mcl_concept_scan_sharded_ex.  Same outputs, bit for bit, as the NCCL paths.
+ */
+size_t mcl_sharded_p2p_block_bytes(int64_t Q, int k, int world);
+int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dtype, int64_t Q,
+                                 int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                                 const float* inv_norm_q, const float* inv_norm_t, float scale,
+                                 int k, int64_t index_base, const int64_t* labels,
+                                 float* topk_val, int64_t* topk_idx, float* row_stats,
+                                 void* workspace, size_t workspace_bytes, void* const* peer_blocks,
+                                 size_t block_bytes, int world, int rank, uint32_t epoch, int flags,
+                                 mcl_stream_t stream);
+
+/*
  * Peer exchange of replicated query batches without SMs.  A sharded scan needs the whole query
  * batch on every GPU; when the batch arrives from the host, every rank uploads 1/N of it over
  * its own PCIe link and PUSHES that slice into the staging buffer of every peer with copy-engine

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcl_sm100.so")
-SOURCES = ["api.cu", "scan_tc.cu", "scan_tc_m0.cu", "scan_tc_m1.cu", "scan_tc_m2.cu", "scan_tc_m3.cu", "gemm_tc.cu", "bwd_simt.cu", "scan_simt.cu", "merge.cu", "select.cu", "panel_scan.cu", "rowops.cu"]
+SOURCES = ["api.cu", "scan_tc.cu", "scan_tc_m0.cu", "scan_tc_m1.cu", "scan_tc_m2.cu", "scan_tc_m3.cu", "gemm_tc.cu", "bwd_simt.cu", "scan_simt.cu", "merge.cu", "select.cu", "panel_scan.cu", "p2p_exchange.cu", "rowops.cu"]
 HEADERS = ["common.cuh", "scan_tc_kernel.cuh", "rownorm.cuh", "rowstate.cuh", "kernels.h", "plan.h", "toplist.cuh", os.path.join("..", "..", "include", "mcl.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

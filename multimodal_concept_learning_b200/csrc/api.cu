@@ -809,6 +809,143 @@ static cu_wait32_t get_wait32() {
   return fn;
 }
 
+// ---- sharded scan with the result exchange over peer memory (p2p_exchange.cu) -------------------
+namespace {
+struct P2PLayout { size_t xcount, fcount, done, mine, xin, fin, bytes; Record rec, mini; int64_t rows; };
+P2PLayout p2p_layout(int64_t Q, int k, int world) {
+  P2PLayout L{};
+  L.rows = Q / world;
+  L.rec = record_layout(Q, k);
+  L.mini = record_layout(L.rows, k);
+  L.xcount = 0; L.fcount = 64; L.done = 128;
+  L.mine = 256;
+  L.xin = L.mine + L.rec.bytes;                            // two receive areas, used in turn (see below)
+  L.fin = L.xin + 2 * L.mini.bytes * (size_t)world;
+  L.bytes = L.fin + L.rec.bytes;
+  return L;
+}
+}  // namespace
+
+size_t mcl_sharded_p2p_block_bytes(int64_t Q, int k, int world) {
+  // 0: this (Q, k, world) cannot use the peer-memory exchange (pieces must be whole 16-byte vectors)
+  if (world < 2 || world > kPushMaxPeers || Q < world || Q % world || k < 1 || ((Q / world) * k) % 4) return 0;
+  return p2p_layout(Q, k, world).bytes;
+}
+
+int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dtype, int64_t Q,
+                                 int64_t V_local, int64_t D, int64_t ldq, int64_t ldt,
+                                 const float* inv_norm_q, const float* inv_norm_t, float scale, int k,
+                                 int64_t index_base, const int64_t* labels, float* topk_val,
+                                 int64_t* topk_idx, float* row_stats, void* workspace,
+                                 size_t workspace_bytes, void* const* peer_blocks, size_t block_bytes,
+                                 int world, int rank, uint32_t epoch, int flags, mcl_stream_t stream) {
+  if (world < 2 || world > kPushMaxPeers || rank < 0 || rank >= world) return fail(MCL_ERR_BAD_ARG, "bad world/rank");
+  if (index_base < 0 || index_base + V_local > (1ll << 32))
+    return fail(MCL_ERR_BAD_ARG, "global table rows must stay below 2^32 (index_base %lld + V_local %lld)",
+                (long long)index_base, (long long)V_local);
+  const size_t need = mcl_sharded_p2p_block_bytes(Q, k, world);
+  if (!need) return fail(MCL_ERR_BAD_ARG, "peer-memory exchange needs Q %% world == 0 and (Q / world) * k %% 4 == 0");
+  if (!peer_blocks || block_bytes < need) return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "peer block %zu B < required %zu B", block_bytes, need);
+  for (int r = 0; r < world; ++r)
+    if (!peer_blocks[r] || !aligned16(peer_blocks[r])) return fail(MCL_ERR_BAD_ARG, "null / unaligned peer block %d", r);
+  if (epoch == 0) return fail(MCL_ERR_BAD_ARG, "epoch counts the scans on these blocks from 1");
+  cu_wait32_t wait32 = get_wait32();
+  if (!wait32) return fail(MCL_ERR_UNIMPLEMENTED, "cuStreamWaitValue32 is not available in this driver");
+  DevInfo di;
+  int rc = require_sm100(&di);
+  if (rc) return rc;
+  const P2PLayout L = p2p_layout(Q, k, world);
+  const Record& rec = L.rec;
+  const Record& mini = L.mini;
+  const int64_t rows = L.rows;
+  char* me = (char*)peer_blocks[rank];
+  char* mine = me + L.mine;
+  cudaStream_t s = (cudaStream_t)stream;
+  // 1. local scan into this rank's record
+  rc = scan_impl(q, table_shard, dtype, Q, V_local, D, ldq, ldt, inv_norm_q, inv_norm_t, scale, k, index_base,
+                 labels, (float*)(mine + rec.val_off), (int64_t*)(mine + rec.idx_off), (float*)(mine + rec.stats_off),
+                 workspace, workspace_bytes, nullptr, s, 0.f,
+                 (flags & MCL_SHARDED_NORMALIZE_Q) ? MCL_SCAN_NORMALIZE_Q : 0);
+  if (rc) return rc;
+  const size_t vb = (size_t)rows * k * 4, ib = (size_t)rows * k * 8, sb = (size_t)rows * 16;
+  // 2. every peer's row range of the record -> that peer's receive area, slot `rank`.  The receive
+  // areas alternate with the epoch: with MCL_SHARDED_LOCAL_ROWS nothing after the merge makes a fast
+  // rank wait for a slow one, but its push of step e+2 needs the slow rank's push of step e+1, which
+  // follows that rank's merge of step e in stream order -- so the area of step e is free by then.
+  const size_t xin_off = L.xin + (size_t)(epoch & 1u) * mini.bytes * (size_t)world;
+  PushParams pp{};
+  pp.npeer = world; pp.self = rank; pp.counter_off = L.xcount; pp.done = (unsigned*)(me + L.done);
+  for (int r = 0; r < world; ++r) pp.peer[r] = (char*)peer_blocks[r];
+  for (int peer = 0; peer < world; ++peer) {
+    const size_t r0 = (size_t)peer * rows, slot = xin_off + mini.bytes * (size_t)rank;
+    const PushSeg segs[3] = {{mine + rec.val_off + r0 * k * 4, slot + mini.val_off, vb},
+                             {mine + rec.idx_off + r0 * k * 8, slot + mini.idx_off, ib},
+                             {mine + rec.stats_off + r0 * 16, slot + mini.stats_off, sb}};
+    for (const PushSeg& sg : segs) { pp.seg[pp.nseg] = sg; pp.seg_peer[pp.nseg] = peer; ++pp.nseg; }
+  }
+  cudaError_t e = launch_p2p_push(pp, di.sm, s);
+  if (e != cudaSuccess) return cuda_fail(e, "p2p push launch");
+  g_launches++;
+  // 3. wait for the other ranks' pieces (a stream memory operation: no SM spins)
+  int wrc = wait32(s, (unsigned long long)(uintptr_t)(me + L.xcount), epoch * (uint32_t)(world - 1), /*GEQ*/ 0u);
+  if (wrc) return fail(MCL_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", wrc);
+  // 4. merge my rows into their place in the result area
+  char* fin = me + L.fin;
+  const size_t o_val = rec.val_off + (size_t)rank * vb, o_idx = rec.idx_off + (size_t)rank * ib,
+               o_st = rec.stats_off + (size_t)rank * sb;
+  char* area = me + xin_off;
+  e = launch_merge_ranks((const float*)(area + mini.val_off), (const int64_t*)(area + mini.idx_off),
+                         (const float*)(area + mini.stats_off), mini.bytes, mini.bytes, mini.bytes, world, rows, k,
+                         (float*)(fin + o_val), (int64_t*)(fin + o_idx), (float*)(fin + o_st), s);
+  if (e != cudaSuccess) return cuda_fail(e, "merge launch");
+  g_launches++;
+  // (the copies out of the result area: ONE launch of the push kernel with the caller's arrays as the
+  // only "peer" -- three cudaMemcpyAsync cost three launches)
+  auto copy_out = [&](const char* s0, char* d0, size_t b0, const char* s1, char* d1, size_t b1, const char* s2,
+                      char* d2, size_t b2) -> cudaError_t {
+    if (!aligned16(d0) || !aligned16(d1) || !aligned16(d2)) {
+      cudaError_t ce = cudaMemcpyAsync(d0, s0, b0, cudaMemcpyDeviceToDevice, s);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d1, s1, b1, cudaMemcpyDeviceToDevice, s);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d2, s2, b2, cudaMemcpyDeviceToDevice, s);
+      return ce;
+    }
+    PushParams pc{};
+    pc.npeer = 1; pc.self = 0; pc.counter_off = 0; pc.done = (unsigned*)(me + L.done);
+    pc.peer[0] = nullptr;                                  // dst_off carries the whole address
+    pc.nseg = 3;
+    pc.seg[0] = PushSeg{s0, (size_t)(uintptr_t)d0, b0};
+    pc.seg[1] = PushSeg{s1, (size_t)(uintptr_t)d1, b1};
+    pc.seg[2] = PushSeg{s2, (size_t)(uintptr_t)d2, b2};
+    g_launches++;
+    return launch_p2p_push(pc, di.sm, s);
+  };
+  if (flags & MCL_SHARDED_LOCAL_ROWS) {   // the caller takes this rank's row range only
+    e = copy_out(fin + o_val, (char*)(topk_val + (size_t)rank * rows * k), vb, fin + o_idx,
+                 (char*)(topk_idx + (size_t)rank * rows * k), ib, fin + o_st, (char*)(row_stats + (size_t)rank * rows * 4), sb);
+    if (e != cudaSuccess) return cuda_fail(e, "copying the merged rows out");
+    return MCL_OK;
+  }
+  // 5. the merged rows -> every other rank's result area, same place
+  PushParams pf{};
+  pf.npeer = world; pf.self = rank; pf.counter_off = L.fcount; pf.done = (unsigned*)(me + L.done);
+  for (int r = 0; r < world; ++r) pf.peer[r] = (char*)peer_blocks[r];
+  for (int peer = 0; peer < world; ++peer) {
+    if (peer == rank) continue;
+    const PushSeg segs[3] = {{fin + o_val, L.fin + o_val, vb}, {fin + o_idx, L.fin + o_idx, ib}, {fin + o_st, L.fin + o_st, sb}};
+    for (const PushSeg& sg : segs) { pf.seg[pf.nseg] = sg; pf.seg_peer[pf.nseg] = peer; ++pf.nseg; }
+  }
+  e = launch_p2p_push(pf, di.sm, s);
+  if (e != cudaSuccess) return cuda_fail(e, "p2p push launch (merged rows)");
+  g_launches++;
+  wrc = wait32(s, (unsigned long long)(uintptr_t)(me + L.fcount), epoch * (uint32_t)(world - 1), /*GEQ*/ 0u);
+  if (wrc) return fail(MCL_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", wrc);
+  // 6. hand the result to the caller's arrays
+  e = copy_out(fin + rec.val_off, (char*)topk_val, (size_t)Q * k * 4, fin + rec.idx_off, (char*)topk_idx,
+               (size_t)Q * k * 8, fin + rec.stats_off, (char*)row_stats, (size_t)Q * 16);
+  if (e != cudaSuccess) return cuda_fail(e, "copying the result out");
+  return MCL_OK;
+}
+
 int mcl_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out) {
   if (!dev_ptr || !ipc_handle_out || bytes == 0) return fail(MCL_ERR_BAD_ARG, "bad peer_alloc args");
   static_assert(sizeof(cudaIpcMemHandle_t) == MCL_IPC_HANDLE_BYTES, "ipc handle size");

@@ -117,6 +117,22 @@ cudaError_t launch_merge_ranks(const float* val, const int64_t* idx, const float
                                int64_t Q, int k, float* out_val, int64_t* out_idx,
                                float* out_stats, cudaStream_t s);
 
+// Peer-memory result exchange of the sharded scan (p2p_exchange.cu): stores `nseg` pieces into the
+// peers' blocks and bumps their arrival counters once every CTA is done.
+struct PushSeg { const char* src; size_t dst_off, bytes; };
+constexpr int kPushMaxPeers = 16;
+constexpr int kPushMaxSegs = 3 * kPushMaxPeers;
+struct PushParams {
+  int nseg, npeer;
+  PushSeg seg[kPushMaxSegs];
+  int seg_peer[kPushMaxSegs];
+  char* peer[kPushMaxPeers];
+  size_t counter_off;
+  unsigned* done;
+  int self;
+};
+cudaError_t launch_p2p_push(const PushParams& p, int sm_count, cudaStream_t s);
+
 cudaError_t launch_row_inv_norm(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld,
                                 float* out, cudaStream_t s);
 cudaError_t launch_gather_mean(const void* table, int dtype, int64_t V, int64_t D, int64_t ld,

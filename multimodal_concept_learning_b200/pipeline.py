@@ -68,7 +68,7 @@ class HostQueryPipeline:
 
     def row_range(self, Q: int) -> Tuple[int, int]:
         """Rows of the batch that the tensors yielded by :meth:`run` hold on this rank."""
-        return self.scanner.local_rows(Q) if self.local_rows else (0, Q)
+        return self.scanner.local_rows_for(Q, self.k) if self.local_rows else (0, Q)
 
     def close(self):
         if self._board is not None:

@@ -59,7 +59,16 @@ class ShardedConceptScan:
     and the reusable gather buffer."""
 
     def __init__(self, table_shard: Tensor, vocab_total: int, *, normalize_t: bool = True,
-                 group=None):
+                 group=None, exchange: str = "auto"):
+        """``exchange``: how the per-rank results meet -- ``"p2p"`` stores them straight into the
+        peers' memory over NVLink (``mcl_concept_scan_sharded_p2p``: two small kernels and two
+        stream waits per scan), ``"nccl"`` uses the library's communicator (one all-gather, or a
+        grouped send/recv + all-gather for world > 2), ``"auto"`` (default) takes the peer-memory
+        path whenever the shape allows it (Q % world == 0, (Q / world) * k % 4 == 0)."""
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        self.exchange = exchange
+        self._boards = {}                 # (Q, k) -> peer-memory blocks of the p2p exchange
         if not table_shard.is_cuda:
             raise RuntimeError("table shard must be a CUDA tensor (no CPU fallback)")
         self.group = group
@@ -90,9 +99,57 @@ class ShardedConceptScan:
                 check(load().mcl_comm_init(uid, self.world, self.rank, C.byref(self._comm)))
 
     def close(self):
+        if getattr(self, "_boards", None):
+            lib = load()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)          # nobody stores into a block that is being freed
+            with torch.cuda.device(self.device):
+                for board in self._boards.values():
+                    for r, p in enumerate(board["ptrs"]):
+                        if r != self.rank and p:
+                            lib.mcl_peer_close(p)
+                    lib.mcl_peer_free(board["base"])
+            self._boards = {}
         if self._comm:
             check(load().mcl_comm_destroy(self._comm))
             self._comm = C.c_void_p(None)
+
+    def _p2p_board(self, Q: int, k: int):
+        """The peer-memory blocks of the result exchange for one (Q, k) shape, or None when the
+        shape (or the ``exchange`` setting) rules the path out.  Creating a board is a collective:
+        every rank reaches it in the same scan."""
+        if self.world < 2 or self.exchange == "nccl":
+            return None
+        key = (int(Q), int(k))
+        board = self._boards.get(key)
+        if board is not None:
+            return board
+        lib = load()
+        nbytes = int(lib.mcl_sharded_p2p_block_bytes(Q, k, self.world))
+        if nbytes == 0:
+            if self.exchange == "p2p":
+                raise ValueError(f"the peer-memory exchange needs Q % world == 0 and (Q / world) * k % 4 == 0 "
+                                 f"(Q={Q}, k={k}, world={self.world})")
+            return None
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(lib.mcl_peer_alloc(nbytes, C.byref(ptr), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        ptrs = [None] * self.world
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs[r] = ptr.value
+                else:
+                    pp = C.c_void_p()
+                    check(lib.mcl_peer_open(h, C.byref(pp)))
+                    ptrs[r] = pp.value
+        dist.barrier(group=self.group)              # every mapping exists before the first store
+        board = {"base": ptr.value, "ptrs": ptrs, "bytes": nbytes, "epoch": 0,
+                 "array": (C.c_void_p * self.world)(*ptrs)}
+        self._boards[key] = board
+        return board
 
     def __del__(self):
         try:
@@ -121,6 +178,15 @@ class ShardedConceptScan:
             return self.rank * per, (self.rank + 1) * per
         return 0, Q
 
+    def local_rows_for(self, Q: int, k: int) -> Tuple[int, int]:
+        """As :meth:`local_rows`, for a scan with this ``k``: the peer-memory exchange splits the rows
+        over the ranks for every world >= 2."""
+        if self.world >= 2 and self.exchange != "nccl" and \
+                int(load().mcl_sharded_p2p_block_bytes(Q, k, self.world)) > 0:
+            per = Q // self.world
+            return self.rank * per, (self.rank + 1) * per
+        return self.local_rows(Q)
+
     def scan(self, q: Tensor, k: int, *, normalize_q: bool = True, scale: float = 1.0,
              labels: Optional[Tensor] = None, label_smoothing: float = 0.0,
              inv_norm_q: Optional[Tensor] = None, local_rows_only: bool = False) -> ops.ScanOutput:
@@ -145,6 +211,19 @@ class ShardedConceptScan:
         val = torch.empty((Q, kk), dtype=torch.float32, device=dev)
         idx = torch.empty((Q, kk), dtype=torch.int64, device=dev)
         stats = torch.empty((Q, 4), dtype=torch.float32, device=dev)
+        board = self._p2p_board(Q, kk)
+        if board is not None:
+            board["epoch"] += 1
+            with torch.cuda.device(dev):
+                ws_bytes = lib.mcl_scan_workspace_bytes(Q, self.hi - self.lo, D, kk, code)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                check(lib.mcl_concept_scan_sharded_p2p(
+                    q.data_ptr(), self.table.data_ptr(), code, Q, self.hi - self.lo, D, q.stride(0),
+                    self.table.stride(0), ops._ptr(inv_norm_q), ops._ptr(self.inv_norm_t), float(scale),
+                    kk, self.lo, ops._ptr(labels), val.data_ptr(), idx.data_ptr(), stats.data_ptr(),
+                    ws.data_ptr(), ws_bytes, board["array"], board["bytes"], self.world, self.rank,
+                    board["epoch"], flags, ops._stream(dev)))
+            return ops.ScanOutput(val, idx, stats, self.vocab_total, labels, float(label_smoothing))
         with torch.cuda.device(dev):
             gbytes = lib.mcl_sharded_gather_bytes(Q, kk, self.world)
             if self._gather is None or self._gather.numel() < gbytes:

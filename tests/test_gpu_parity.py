@@ -321,10 +321,24 @@ def test_full_size_properties_qwen2vl_scale(mcl):
     assert not (differ & (mv != mv[:, -1:])).any()
     assert float(differ.float().mean()) < 1e-4
     torch.testing.assert_close(ms[:, 0] + torch.log(ms[:, 1]), full.lse, rtol=1e-6, atol=1e-5)
-    sub = slice(4000, 4032)
-    z = torch.nn.functional.normalize(q[sub].float(), dim=1) @ torch.nn.functional.normalize(t.float(), dim=1).T
-    check_topk(full.topk_val[sub], full.topk_idx[sub], z, k, rtol=RTOL, atol=1e-5)
-    torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4)
+    # 256 rows spread over all row blocks against torch fp32 on the GPU, 64 at a time: top-k,
+    # log-sum-exp, sum of the scores (the label-smoothing input), the label's score and the loss
+    labels = torch.randint(0, V, (Q,), generator=g, device="cuda")
+    lab = mcl.concept_scan(q, t, k, inv_norm_t=inv_t, labels=labels, label_smoothing=0.1)
+    assert torch.equal(lab.topk_idx, full.topk_idx) and torch.equal(lab.topk_val, full.topk_val)
+    tn = torch.nn.functional.normalize(t.float(), dim=1)
+    rows = torch.linspace(0, Q - 1, 256).long().cuda()
+    for c in range(0, 256, 64):
+        sub = rows[c:c + 64]
+        z = torch.nn.functional.normalize(q[sub].float(), dim=1) @ tn.T
+        check_topk(full.topk_val[sub], full.topk_idx[sub], z, k, rtol=RTOL, atol=1e-5)
+        torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4)
+        torch.testing.assert_close(lab.stats[sub, 2], z.sum(1), rtol=RTOL, atol=2e-2)      # |sum| ~ sqrt(V) * 0.017
+        torch.testing.assert_close(lab.stats[sub, 3], z[torch.arange(64), labels[sub]], rtol=RTOL, atol=1e-5)
+        want = torch.nn.functional.cross_entropy(z, labels[sub], label_smoothing=0.1, reduction="none")
+        torch.testing.assert_close(lab.loss_rows[sub], want, rtol=RTOL, atol=1e-4)
+        del z
+    del tn
 
 
 @pytest.mark.parametrize("name,Q,V,D,scale", [("c4", 65536, 128256, 4096, 1.0),
@@ -353,15 +367,20 @@ def test_full_size_multi_wave_plans(mcl, name, Q, V, D, scale):
                                rtol=RTOL, atol=0)
     assert (full.topk_val[:, 1:] <= full.topk_val[:, :-1]).all()
     assert int(full.topk_idx.min()) >= 0 and int(full.topk_idx.max()) < V
-    sub = rows[::5][:48]
     tn = torch.nn.functional.normalize(t.float(), dim=1)
-    z = scale * (torch.nn.functional.normalize(q[sub].float(), dim=1) @ tn.T)
+    picked = rows[torch.linspace(0, rows.numel() - 1, 192).long().cuda()]      # 192 rows, 48 at a time
+    for c in range(0, 192, 48):
+        sub = picked[c:c + 48]
+        z = scale * (torch.nn.functional.normalize(q[sub].float(), dim=1) @ tn.T)
+        check_topk(full.topk_val[sub], full.topk_idx[sub], z, k, rtol=RTOL, atol=1e-5 * scale)
+        torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4 * scale)
+        torch.testing.assert_close(full.stats[sub, 3], z[torch.arange(sub.numel()), labels[sub]], rtol=RTOL,
+                                   atol=1e-5 * scale)
+        torch.testing.assert_close(full.stats[sub, 2], z.sum(1), rtol=RTOL, atol=2e-2 * scale)
+        want = torch.nn.functional.cross_entropy(z, labels[sub], reduction="none")
+        torch.testing.assert_close(full.loss_rows[sub], want, rtol=RTOL, atol=1e-4 * scale)
+        del z
     del tn
-    check_topk(full.topk_val[sub], full.topk_idx[sub], z, k, rtol=RTOL, atol=1e-5 * scale)
-    torch.testing.assert_close(full.lse[sub], torch.logsumexp(z, 1), rtol=RTOL, atol=1e-4 * scale)
-    torch.testing.assert_close(full.stats[sub, 3], z[torch.arange(sub.numel()), labels[sub]], rtol=RTOL,
-                               atol=1e-5 * scale)
-    del z
     old = mcl.set_option(7, 0)
     try:
         other = mcl.concept_scan(q, t, k, inv_norm_t=inv_t, scale=scale, labels=labels)

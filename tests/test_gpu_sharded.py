@@ -27,7 +27,7 @@ def _inputs(Q=304):
     return q, t, labels, k
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, exchange="auto"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -38,7 +38,7 @@ def _worker(rank, world, port, ret):
         q, t, labels, k = _inputs()
         qd, td, ld = q.cuda(), t.cuda(), labels.cuda()
         lo, hi = shard_rows(t.shape[0], world, rank)
-        sc = ShardedConceptScan(td[lo:hi].contiguous(), t.shape[0])
+        sc = ShardedConceptScan(td[lo:hi].contiguous(), t.shape[0], exchange=exchange)
         for _ in range(3):                           # reuse of the communicator and gather buffer
             out = sc.scan(qd, k, scale=20.0, labels=ld, label_smoothing=0.1)
         full = mcl.concept_scan(qd, td, k, scale=20.0, labels=ld, label_smoothing=0.1)
@@ -72,7 +72,8 @@ def _worker(rank, world, port, ret):
         # more batches than staging slots, so the slot ring wraps
         pipe = HostQueryPipeline(td[lo:hi], k, scale=20.0, scanner=sc, local_rows=True, lag=2)
         r0, r1 = pipe.row_range(qh.shape[0])
-        assert (r0, r1) == ((rank * 304 // world, (rank + 1) * 304 // world) if world > 2 else (0, 304))
+        split = world > 2 or exchange != "nccl"          # the peer-memory exchange splits the rows at world 2 too
+        assert (r0, r1) == ((rank * 304 // world, (rank + 1) * 304 // world) if split else (0, 304))
         flipped = qh.flip(0).contiguous().pin_memory()
         got = list(pipe.run([qh, flipped] * 6))
         assert len(got) == 12
@@ -100,13 +101,17 @@ def test_world1_sharded_equals_plain(lib_built):
     torch.testing.assert_close(out.stats, full.stats, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])   # 2: all-gather merge; 4, 8: row-exchange merge
-def test_multi_rank_nccl_sharded_equals_unsharded(lib_built, world):
+# "auto": the result exchange over peer memory (mcl_concept_scan_sharded_p2p) wherever the shape allows
+# it -- the 304-row scans with k = 50, and k = 1 at worlds 2 and 4 -- and NCCL elsewhere (301 rows; k = 1 at
+# world 8); "nccl": 2 = all-gather merge; 4, 8 = row-exchange merge
+@pytest.mark.parametrize("exchange", ["auto", "nccl"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_nccl_sharded_equals_unsharded(lib_built, world, exchange):
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs >= {world} GPUs")
     port = _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, exchange), nprocs=world, join=True)
         assert dict(ret) == {r: "ok" for r in range(world)}
