@@ -198,6 +198,9 @@ __device__ __forceinline__ void bulk_row_g2s(uint32_t dst_smem, const void* src,
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -284,6 +287,12 @@ gather_mean_bulk_kernel(const T* __restrict__ table, long long V, int D, long lo
       const int nvl = (nvec + 31) >> 5;
       T* o = out + row * ld_out;
       float inv = 1.f;
+      // With normalisation the fp32 means of rows of two or more tokens are parked in the slots they
+      // came from between the two passes (a lane overwrites exactly the 16 bytes per slot it has just
+      // read: 8 bf16 in, 2 x 4 fp32 out), so the second pass is a load, a scale and a store.
+      const bool stash = normalize && n >= 2;
+      const uint32_t s_a = slot0 + cs * slot_stride;
+      const uint32_t s_b = slot0 + (cs + 1 == (uint32_t)S ? 0u : cs + 1) * slot_stride;
       for (int pass = normalize ? 0 : 1; pass < 2; ++pass) {
         float ss = 0.f;
 #pragma unroll 1
@@ -292,32 +301,52 @@ gather_mean_bulk_kernel(const T* __restrict__ table, long long V, int D, long lo
           float acc[N];
 #pragma unroll
           for (int c = 0; c < N; ++c) acc[c] = 0.f;
-          if (v < nvec) {
-            uint32_t sj = cs;
-            for (int j = 0; j < n; ++j) {
-              float x[N];
-              Vec<T>::widen(lds_v4(slot0 + sj * slot_stride + (uint32_t)v * 16u), x);
-#pragma unroll
-              for (int c = 0; c < N; ++c) acc[c] += x[c];
-              if (++sj == (uint32_t)S) sj = 0;
+          if (pass == 1 && stash) {
+            if (v < nvec) {
+              const uint4 lo = lds_v4(s_a + (uint32_t)v * 16u);
+              acc[0] = __uint_as_float(lo.x); acc[1] = __uint_as_float(lo.y);
+              acc[2] = __uint_as_float(lo.z); acc[3] = __uint_as_float(lo.w);
+              if (N == 8) {
+                const uint4 hi = lds_v4(s_b + (uint32_t)v * 16u);
+                acc[N - 4] = __uint_as_float(hi.x); acc[N - 3] = __uint_as_float(hi.y);
+                acc[N - 2] = __uint_as_float(hi.z); acc[N - 1] = __uint_as_float(hi.w);
+              }
             }
-          }
-          if (n > 1) {                               // (uniform) exact x / n, see div_by_count
-            float q[N];
-            bool odd = false;
+          } else {
+            if (v < nvec) {
+              uint32_t sj = cs;
+              for (int j = 0; j < n; ++j) {
+                float x[N];
+                Vec<T>::widen(lds_v4(slot0 + sj * slot_stride + (uint32_t)v * 16u), x);
 #pragma unroll
-            for (int c = 0; c < N; ++c) {
-              const float q0 = acc[c] * rn;
-              q[c] = fmaf(fmaf(-fn, q0, acc[c]), rn, q0);
-              const float ax = fabsf(acc[c]);
-              odd = odd || (!(ax > 1e-30f && ax < 1e30f) && acc[c] != 0.f);
+                for (int c = 0; c < N; ++c) acc[c] += x[c];
+                if (++sj == (uint32_t)S) sj = 0;
+              }
             }
-            if (__any_sync(0xffffffffu, odd)) {
+            if (n > 1) {                             // (uniform) exact x / n, see the note above the kernel
+              float q[N];
+              bool odd = false;
 #pragma unroll
-              for (int c = 0; c < N; ++c) q[c] = acc[c] / fn;
+              for (int c = 0; c < N; ++c) {
+                const float q0 = acc[c] * rn;
+                q[c] = fmaf(fmaf(-fn, q0, acc[c]), rn, q0);
+                const float ax = fabsf(acc[c]);
+                odd = odd || (!(ax > 1e-30f && ax < 1e30f) && acc[c] != 0.f);
+              }
+              if (__any_sync(0xffffffffu, odd)) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) q[c] = acc[c] / fn;
+              }
+#pragma unroll
+              for (int c = 0; c < N; ++c) acc[c] = q[c];
             }
-#pragma unroll
-            for (int c = 0; c < N; ++c) acc[c] = q[c];
+            if (pass == 0 && stash && v < nvec) {
+              sts_v4(s_a + (uint32_t)v * 16u, make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]),
+                                                         __float_as_uint(acc[2]), __float_as_uint(acc[3])));
+              if (N == 8)
+                sts_v4(s_b + (uint32_t)v * 16u, make_uint4(__float_as_uint(acc[N - 4]), __float_as_uint(acc[N - 3]),
+                                                           __float_as_uint(acc[N - 2]), __float_as_uint(acc[N - 1])));
+            }
           }
           if (pass == 0) {
 #pragma unroll

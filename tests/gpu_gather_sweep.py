@@ -20,7 +20,8 @@ for V, D in [(152064, 3584), (152064, 2048)]:
         for variant in (0, 1):
             old = mcl.set_option(17, variant)
             ms = timed(lambda: mcl.gather_mean(table, offs, ids, False, validate=False))
+            msn = timed(lambda: mcl.gather_mean(table, offs, ids, True, validate=False))
             mcl.set_option(17, old)
-            line += f"  v{variant} {ms * 1e3:7.1f} us {b / ms / 1e6:5.0f} GB/s"
+            line += f"  v{variant} {ms * 1e3:7.1f} us {b / ms / 1e6:5.0f} GB/s (normalised {msn * 1e3:7.1f} us {b / msn / 1e6:5.0f})"
         print(line, flush=True)
     del table
