@@ -221,6 +221,22 @@ int mcl_ce_backward(const void* q /*[n,D]*/, const void* table /*[V,D]*/, int dt
                     void* workspace, size_t workspace_bytes, mcl_stream_t stream);
 
 /*
+ * Same, with the table gradient's dtype: MCL_DTYPE_BF16 (bf16 inputs, D % 8 == 0, and all n rows in
+ * one row block: n <= mcl_ce_backward_block_rows(n, V, dtype)) makes the last GEMM round its fp32
+ * accumulators once and write [V, D] bf16 -- half the bytes of the backward's largest write and no
+ * cast pass for a bf16 parameter.  With few rows (the reference's answer-only supervision: ~24 of
+ * 1672 positions carry a label) dL/dq = dL/dz * T has a handful of output tiles and K = V: its K
+ * range is split over the SMs and the partial products are added with atomics (the summation order
+ * of grad_q is then not fixed from run to run; rtol 1e-6).
+ */
+int64_t mcl_ce_backward_block_rows(int64_t n, int64_t V, int dtype);
+int mcl_ce_backward_ex(const void* q, const void* table, int dtype, int64_t n, int64_t V, int64_t D,
+                       int64_t ldq, int64_t ldt, const float* lse, const int64_t* labels, float scale,
+                       float softcap, float label_smoothing, int64_t vocab_total, const float* grad_loss,
+                       int64_t n_valid, float* grad_q, void* grad_table, int grad_table_dtype,
+                       void* workspace, size_t workspace_bytes, mcl_stream_t stream);
+
+/*
  * The GEMM of that backward on its own: C[M,N] fp32 (+)= A * B, bf16 operands on tcgen05.
  * a_mn = 0: A is stored [M][K] (pitch lda); a_mn = 1: A is stored [K][M].  Same for B with N.
  */

@@ -54,6 +54,9 @@ SIGNATURES = {
     "mcl_ce_backward_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "mcl_ce_backward": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _f32, _f32,
                                _i64, _ptr, _i64, _ptr, _ptr, _ptr, _sz, _ptr]),
+    "mcl_ce_backward_block_rows": (_i64, [_i64, _i64, _i32]),
+    "mcl_ce_backward_ex": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _f32, _f32,
+                                  _i64, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _sz, _ptr]),
     "mcl_gemm_bf16": (_i32, [_ptr, _i32, _i64, _ptr, _i32, _i64, _ptr, _i64, _i64, _i64, _i64, _i32, _ptr]),
     "mcl_comm_unique_id": (_i32, [_ptr]),
     "mcl_comm_init": (_i32, [_ptr, _i32, _i32, C.POINTER(_ptr)]),

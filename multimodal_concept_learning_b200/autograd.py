@@ -47,10 +47,16 @@ class FusedScanCrossEntropy(torch.autograd.Function):
         n = int(rows.numel())
         V, D = table.shape
         gq = torch.zeros(q.shape, dtype=torch.float32, device=dev) if need_q else None
+        lib = load()
+        # A bf16 table whose labelled rows fit one row block of the backward (<= 4096: the reference's
+        # answer-only supervision labels ~1 % of the positions) gets its gradient in bf16 straight from
+        # the last GEMM's epilogue: half the bytes of the step's largest write, no fp32 -> bf16 pass.
+        gt_bf16 = bool(need_t and n > 0 and table.dtype == torch.bfloat16 and D % 8 == 0 and
+                       n <= int(lib.mcl_ce_backward_block_rows(n, V, 0)))
         # (the library writes every element of the table gradient: no memset of [V, D] when n > 0)
-        gt = (torch.empty if n > 0 else torch.zeros)((V, D), dtype=torch.float32, device=dev) if need_t else None
+        gt = (torch.empty if n > 0 else torch.zeros)((V, D), dtype=torch.bfloat16 if gt_bf16 else torch.float32,
+                                                      device=dev) if need_t else None
         if n > 0:
-            lib = load()
             qv = ops._rowmajor(q.detach()[rows])              # the rows that carry a label
             tb = ops._rowmajor(table.detach())
             lse_v = lse[rows].contiguous()
@@ -61,10 +67,10 @@ class FusedScanCrossEntropy(torch.autograd.Function):
             with torch.cuda.device(dev):
                 ws_bytes = lib.mcl_ce_backward_workspace_bytes(n, V, D, code)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                check(lib.mcl_ce_backward(qv.data_ptr(), tb.data_ptr(), code, n, V, D, qv.stride(0), tb.stride(0),
-                                          lse_v.data_ptr(), lab_v.data_ptr(), ctx.scale, ctx.softcap, ctx.eps, V,
-                                          g.data_ptr(), n, ops._ptr(gq_v), ops._ptr(gt), ws.data_ptr(), ws_bytes,
-                                          ops._stream(dev)))
+                check(lib.mcl_ce_backward_ex(qv.data_ptr(), tb.data_ptr(), code, n, V, D, qv.stride(0), tb.stride(0),
+                                             lse_v.data_ptr(), lab_v.data_ptr(), ctx.scale, ctx.softcap, ctx.eps, V,
+                                             g.data_ptr(), n, ops._ptr(gq_v), ops._ptr(gt), 0 if gt_bf16 else 1,
+                                             ws.data_ptr(), ws_bytes, ops._stream(dev)))
             if need_q:
                 gq[rows] = gq_v
         return (gq.to(q.dtype) if need_q else None, gt.to(table.dtype) if need_t else None,

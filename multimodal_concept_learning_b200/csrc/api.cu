@@ -534,12 +534,34 @@ size_t mcl_ce_backward_workspace_bytes(int64_t n, int64_t V, int64_t D, int dtyp
   return (size_t)((bwd_blocking(n, V, dtype).p_bytes + 255) & ~(int64_t)255);
 }
 
+int64_t mcl_ce_backward_block_rows(int64_t n, int64_t V, int dtype) {
+  if (n <= 0 || V <= 0) return 0;
+  return bwd_blocking(n, V, dtype).nb;
+}
+
 int mcl_ce_backward(const void* q, const void* table, int dtype, int64_t n, int64_t V, int64_t D, int64_t ldq,
                     int64_t ldt, const float* lse, const int64_t* labels, float scale, float softcap,
                     float label_smoothing, int64_t vocab_total, const float* grad_loss, int64_t n_valid,
                     float* grad_q, float* grad_table, void* workspace, size_t workspace_bytes,
                     mcl_stream_t stream_) {
+  return mcl_ce_backward_ex(q, table, dtype, n, V, D, ldq, ldt, lse, labels, scale, softcap, label_smoothing,
+                            vocab_total, grad_loss, n_valid, grad_q, grad_table, MCL_DTYPE_F32, workspace,
+                            workspace_bytes, stream_);
+}
+
+int mcl_ce_backward_ex(const void* q, const void* table, int dtype, int64_t n, int64_t V, int64_t D, int64_t ldq,
+                       int64_t ldt, const float* lse, const int64_t* labels, float scale, float softcap,
+                       float label_smoothing, int64_t vocab_total, const float* grad_loss, int64_t n_valid,
+                       float* grad_q, void* grad_table_, int grad_table_dtype, void* workspace,
+                       size_t workspace_bytes, mcl_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  float* grad_table = (float*)grad_table_;
+  if (grad_table_dtype != MCL_DTYPE_F32 && grad_table_dtype != MCL_DTYPE_BF16)
+    return fail(MCL_ERR_BAD_ARG, "grad_table_dtype %d", grad_table_dtype);
+  const bool gt_bf16 = grad_table_ && grad_table_dtype == MCL_DTYPE_BF16;
+  if (gt_bf16 && (dtype != MCL_DTYPE_BF16 || n > mcl_ce_backward_block_rows(n, V, dtype) || (D % 8)))
+    return fail(MCL_ERR_BAD_ARG, "a bf16 table gradient needs bf16 inputs, D %% 8 == 0 and all %lld rows in one block "
+                "of mcl_ce_backward_block_rows (no accumulation across row blocks)", (long long)n);
   if (dtype != MCL_DTYPE_BF16 && dtype != MCL_DTYPE_F32) return fail(MCL_ERR_BAD_ARG, "dtype %d", dtype);
   if (n < 0 || V < 1 || D < 1 || ldq < D || ldt < D || vocab_total < 1 || n_valid < 1)
     return fail(MCL_ERR_BAD_ARG, "bad shape n=%lld V=%lld D=%lld", (long long)n, (long long)V, (long long)D);
@@ -612,8 +634,11 @@ int mcl_ce_backward(const void* q, const void* table, int dtype, int64_t n, int6
         g_launches++;
       }
       if (grad_table) {
-        e = launch_gemm_tc(workspace, 1, bl.vc, qb + r0 * ldq, 1, ldq, grad_table + v0 * D, D, vc, D, rows, r0 > 0,
-                           di.sm, stream);
+        // (one row block: the product is final -- with a bf16 gradient the accumulators are rounded once
+        // on the way out, half the bytes of the largest write of the backward and no cast pass after it)
+        float* gt_chunk = gt_bf16 ? (float*)((__nv_bfloat16*)grad_table_ + v0 * D) : grad_table + v0 * D;
+        e = launch_gemm_tc(workspace, 1, bl.vc, qb + r0 * ldq, 1, ldq, gt_chunk, D, vc, D, rows, r0 > 0,
+                           di.sm, stream, gt_bf16 ? 1 : 0);
         if (e != cudaSuccess) return cuda_fail(e, "backward dL/dT GEMM launch");
         g_launches++;
       }

@@ -36,10 +36,17 @@ constexpr uint32_t kMnGroupBytes = 64 * kBlockK * 2;      // one 64 x 64 box of 
 
 struct GemmParams {
   int M, N, K;
-  float* C;
+  float* C;              // fp32 output; or bf16 (out_bf16) -- then the pointer is a __nv_bfloat16*
   long long ldc;
   int accumulate;        // 1: C += A*B, 0: C = A*B
   int m_tiles, n_tiles;
+  // split K: work item w = (tile w % tiles, K blocks [ (w / tiles) * kb_per, ... + kb_per) ); with
+  // ksplit > 1 the partial products are added with red.global.add.f32 (C zeroed by the launcher).
+  // A product with few output tiles and a long K -- dL/dq = P T for a handful of labelled rows: 5
+  // tiles, K = 262 k table rows -- otherwise runs on 5 of 148 SMs (measured: 1357 us of a 2.5 ms
+  // backward at the reference's native shape).
+  int ksplit, kb_per;
+  int out_bf16;          // round the fp32 accumulators to bf16 on the way out (ksplit = 1, no accumulate)
 };
 
 // MN-major SWIZZLE_128B operand: LBO = 8 KB between 64-wide M/N groups, SBO = 1 KB between 8-row K groups
@@ -85,13 +92,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
   const int tiles = p.m_tiles * p.n_tiles;
+  const int items = tiles * p.ksplit;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int t = w % tiles, ks = w / tiles;
         const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;     // tiles of one row block run side by side
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_backoff(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * kGemmStageBytes;
           const uint32_t sb = sa + kGemmABytes;
@@ -120,11 +130,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kBlockN) | (kAMN ? (1u << 15) : 0u) | (kBMN ? (1u << 16) : 0u);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int kb0 = (w / tiles) * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
         mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBlockN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kGemmStageBytes;
@@ -135,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             // K-major: +32 B inside the 128 B row; MN-major: +16 rows of 128 B (units of 16 B)
             const uint64_t ad = adesc + (kAMN ? 128u * k : 2u * k);
             const uint64_t bd = bdesc + (kBMN ? 128u * k : 2u * k);
-            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(kb != kb0 || k != 0));
           }
           umma_commit(empty_bar(stage));
           if (++stage == kGemmStages) { stage = 0; phase ^= 1u; }
@@ -148,7 +159,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     constexpr int kHalfN = kBlockN / 2;
     uint32_t acc = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int t = w % tiles;
       const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
       const long long row = (long long)mb * kBlockM + quarter * 32 + lane;
       const int col_base = nb * kBlockN + half * kHalfN;
@@ -168,7 +180,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         const int col0 = col_base + c * kChunk;
-        if (row < p.M && col0 < p.N) {
+        if (row < p.M && col0 < p.N && p.out_bf16) {
+          __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc;
+          if (col0 + kChunk <= p.N && (p.ldc & 7) == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(brow + col0);
+#pragma unroll
+            for (int i = 0; i < kChunk / 8; ++i) {
+              uint4 v;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(y[8 * i + 2 * j], y[8 * i + 2 * j + 1]);
+              dst[i] = v;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i)
+              if (col0 + i < p.N) brow[col0 + i] = __float2bfloat16_rn(y[i]);
+          }
+        } else if (row < p.M && col0 < p.N && p.ksplit > 1) {
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i)
+            if (col0 + i < p.N) atomicAdd(crow + col0 + i, y[i]);   // (result unused: red.global.add.f32)
+        } else if (row < p.M && col0 < p.N) {
           if (col0 + kChunk <= p.N && (p.ldc & 3) == 0) {
             float4* dst = reinterpret_cast<float4*>(crow + col0);
 #pragma unroll
@@ -201,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // C[M,N] (+)= A * B.  a: K-major -> [M][K] with pitch lda, MN-major -> [K][M] with pitch lda; same for b.
 cudaError_t launch_gemm_tc(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb,
                            float* c, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate,
-                           int sm_count, cudaStream_t s) {
+                           int sm_count, cudaStream_t s, int out_bf16) {
   if (M == 0 || N == 0) return cudaSuccess;
   static std::atomic<bool> attr_set[64];
   int dev = 0;
@@ -225,7 +258,22 @@ cudaError_t launch_gemm_tc(const void* a, int a_mn, int64_t lda, const void* b, 
   p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
   p.n_tiles = (int)((N + kBlockN - 1) / kBlockN);
   const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count ? tiles : sm_count;
+  const int num_kb = (int)((K + kBlockK - 1) / kBlockK);
+  p.out_bf16 = out_bf16;
+  p.ksplit = 1; p.kb_per = num_kb;
+  if (!out_bf16 && tiles * 2 <= sm_count && num_kb >= 16) {       // few output tiles, long K: split K over the idle SMs
+    int ks = sm_count / tiles;
+    if (ks > num_kb / 4) ks = num_kb / 4;
+    p.kb_per = (num_kb + ks - 1) / ks;
+    p.ksplit = (num_kb + p.kb_per - 1) / p.kb_per;                 // no empty split
+    if (p.ksplit > 1 && !accumulate) {
+      cudaError_t e = cudaMemset2DAsync(c, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  if (out_bf16 && accumulate) return cudaErrorInvalidValue;
+  const int items = tiles * p.ksplit;
+  const int grid = items < sm_count ? items : sm_count;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);

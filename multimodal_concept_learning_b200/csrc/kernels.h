@@ -69,9 +69,12 @@ Workspace carve_workspace(void* base, int nslots, int num_rb, int nctr, size_t e
 // 2-D bf16 row-major [rows, cols] (pitch ld elements) -> TMA tiles of box_rows x 64, SWIZZLE_128B
 bool make_tmap_bf16(::CUtensorMap_st* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 // C[M,N] fp32 (+)= A * B on tcgen05 (gemm_tc.cu); *_mn = 1: the operand is stored [K][M or N]
+// (few output tiles and a long K: K is split over the SMs and the partial products are added with
+// atomics -- the summation order of such a product is not fixed; out_bf16: c is a __nv_bfloat16*, pitch
+// ldc elements, the fp32 accumulators are rounded once on the way out -- not with accumulate)
 cudaError_t launch_gemm_tc(const void* a, int a_mn, int64_t lda, const void* b, int b_mn, int64_t ldb,
                            float* c, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate,
-                           int sm_count, cudaStream_t s);
+                           int sm_count, cudaStream_t s, int out_bf16 = 0);
 // fp32 check path of the backward (bwd_simt.cu): C (+)= op(A) * op(B) with arbitrary strides, and Z -> dL/dz in place
 cudaError_t launch_gemm_simt(const float* a, int64_t sa_m, int64_t sa_k, const float* b, int64_t sb_k, int64_t sb_n,
                              float* c, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate, cudaStream_t s);

@@ -359,11 +359,13 @@ def test_gemm_bf16_all_operand_layouts(a_mn, b_mn, M, N, K):
 
 @pytest.mark.parametrize("Q,V,D,eps,cap", [(700, 9000, 128, 0.1, None), (300, 50000, 64, 0.0, None),
                                            (5000, 20000, 64, 0.1, None), (260, 3000, 72, 0.0, 6.0),
-                                           (24, 262235, 1152, 0.0, None)])
+                                           (24, 262235, 1152, 0.0, None), (9000, 6000, 64, 0.0, None)])
 def test_f1_native_backward_blocks_and_chunks(Q, V, D, eps, cap):
     """bf16 backward on the tensor cores across the library's blocking: several row blocks, several
     table chunks (V beyond one dL/dz block), several blocks of 4096 rows, soft-capped logits, and the
-    reference's own shape (a few labelled rows against the Gemma-3 table).  Reference: torch autograd
+    reference's own shape (a few labelled rows against the Gemma-3 table: dL/dq with its K range split
+    over the SMs, the table gradient written in bf16 by the GEMM), 6750 labelled rows (two row blocks:
+    the fp32 table gradient accumulates across them).  Reference: torch autograd
     in fp32 through F.cross_entropy(softcap(h @ E^T)) on the same bf16 values."""
     from multimodal_concept_learning_b200.autograd import fused_cross_entropy
     g = torch.Generator(device="cuda").manual_seed(Q + V)
