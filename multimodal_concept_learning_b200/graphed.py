@@ -58,8 +58,11 @@ class GraphedConceptScan:
             raise ValueError(f"graph was captured for q {tuple(self.q.shape)}, got {tuple(q.shape)}")
         if (labels is None) != (self.labels is None):
             raise ValueError("labels must be given exactly when the graph was captured with_labels")
-        self.q.copy_(q, non_blocking=True)
-        if labels is not None:
+        # (a caller that fills `scan.q` / `scan.labels` in place -- e.g. the producer kernel writes the
+        # concept embeddings straight into the graph's buffer -- passes them back and pays no copy)
+        if q.data_ptr() != self.q.data_ptr():
+            self.q.copy_(q, non_blocking=True)
+        if labels is not None and labels.data_ptr() != self.labels.data_ptr():
             self.labels.copy_(labels, non_blocking=True)
         self.graph.replay()
         return self.out

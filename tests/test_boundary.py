@@ -82,6 +82,41 @@ def test_argument_validation_needs_no_device(lib_built):
     assert lib.mcl_sharded_gather_bytes(100, 50, 8) >= 8 * (100 * 50 * 12 + 1600)
 
 
+def test_host_only_sizing_of_the_round2_entry_points(lib_built):
+    """Sizing / eligibility functions that need no device: the peer-memory exchange of the sharded
+    scan, the row blocking of the backward, and the argument checks in front of both."""
+    from multimodal_concept_learning_b200 import _lib
+    lib = _lib.load()
+    # peer-memory exchange: world 2..16, Q % world == 0, (Q / world) * k % 4 == 0
+    assert lib.mcl_sharded_p2p_block_bytes(8192, 50, 8) > 8192 * (12 * 50 + 16) * 2
+    assert lib.mcl_sharded_p2p_block_bytes(304, 50, 2) > 0 and lib.mcl_sharded_p2p_block_bytes(304, 50, 8) > 0
+    assert lib.mcl_sharded_p2p_block_bytes(301, 50, 2) == 0          # rows do not divide
+    assert lib.mcl_sharded_p2p_block_bytes(304, 1, 8) == 0           # 38 rows x k = 1: pieces are not 16-byte multiples
+    assert lib.mcl_sharded_p2p_block_bytes(304, 50, 1) == 0 and lib.mcl_sharded_p2p_block_bytes(3400, 50, 17) == 0
+    # record of all rows + two receive areas (world slots of Q / world rows each) + result area = 4 records
+    assert lib.mcl_sharded_p2p_block_bytes(8192, 50, 8) >= 4 * 8192 * (12 * 50 + 16)
+    buf = C.create_string_buffer(4096)
+    p16 = (C.addressof(buf) + 15) & ~15
+    blocks = (C.c_void_p * 2)(p16, p16)
+    def p2p(world=2, rank=0, epoch=1, Q=304, block_bytes=1 << 30, k=50):
+        return lib.mcl_concept_scan_sharded_p2p(p16, p16, 0, Q, 3000, 64, 64, 64, None, None, 1.0, k, 0, None, p16, p16,
+                                                p16, p16, 4096, blocks, block_bytes, world, rank, epoch, 0, None)
+    assert p2p(world=1) == -1 and p2p(rank=2) == -1
+    assert p2p(Q=301) == -1 and "Q % world" in _lib.last_error()
+    assert p2p(block_bytes=64) == -4                                  # MCL_ERR_WORKSPACE_TOO_SMALL
+    assert p2p(epoch=0) == -1 and "epoch" in _lib.last_error()
+    # backward: rows per block (<= 4096, whole row blocks of 128), and the bf16-gradient precondition
+    assert lib.mcl_ce_backward_block_rows(24, 262235, 0) == 128
+    assert lib.mcl_ce_backward_block_rows(6750, 6000, 0) == 4096
+    assert lib.mcl_ce_backward_block_rows(0, 10, 0) == 0
+    def bwd(n, gt_dtype, D=64, dtype=0):
+        return lib.mcl_ce_backward_ex(p16, p16, dtype, n, 6000, D, D, D, p16, p16, 1.0, 0.0, 0.0, 6000, p16, n, None,
+                                      p16, gt_dtype, p16, 4096, None)
+    assert bwd(6750, 0) == -1 and "one block" in _lib.last_error()    # bf16 gradient across two row blocks
+    assert bwd(100, 0, dtype=1) == -1                                 # ... or from fp32 inputs
+    assert bwd(100, 7) == -1 and "grad_table_dtype" in _lib.last_error()
+
+
 @pytest.mark.parametrize("shape", [(16, 50257, 768), (4096, 49408, 768), (8192, 152064, 3584),
                                    (65536, 128256, 4096), (32768, 1048576, 1024), (8192, 19008, 3584),
                                    (1, 1, 8), (129, 257, 72), (700, 3000, 64), (300, 5000, 768),
