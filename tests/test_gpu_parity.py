@@ -592,6 +592,30 @@ def test_merge_select_then_sort_equals_streaming_fold(mcl, Q, V, D, k, kind):
             assert torch.equal(a.topk_idx[sub].cpu(), ref.topk_idx)
 
 
+@pytest.mark.parametrize("Q", [300, 2304])
+def test_streaming_filter_with_large_tie_groups_at_the_threshold(mcl, Q):
+    """k = 64 with far more than 129 - k exact ties at the k-th place.  Scores take only
+    20 distinct values, 250 table rows each, so every threshold the streaming filter ever holds
+    sits inside a tie group of 250, compactions included; the answer is decided by the
+    lowest-row rule alone.  Raw dot products of bf16-exact integers: exact expected output.
+    (300 rows: merge_slots_kernel; 2304 rows: merge_rows_kernel.)"""
+    V, D, k = 5000, 16, 64
+    j = torch.arange(V)
+    val = (j % 20).float()
+    t = torch.zeros(V, D)
+    t[:, 0] = val
+    mult = torch.tensor([1.0, 2.0, -1.0, 3.0, -2.0])[torch.arange(Q) % 5]
+    q = torch.zeros(Q, D)
+    q[:, 0] = mult
+    out = mcl.concept_scan(q.bfloat16().cuda(), t.bfloat16().cuda(), k, normalize_q=False, normalize_t=False)
+    top_pos = (torch.arange(k) * 20 + 19)            # the 64 lowest rows with the largest value
+    top_neg = torch.arange(k) * 20                   # ... with the smallest value (negative multipliers)
+    want_idx = torch.where((mult > 0)[:, None], top_pos[None, :], top_neg[None, :])
+    want_val = torch.where(mult > 0, 19.0 * mult, torch.zeros(Q))[:, None].expand(Q, k)
+    assert torch.equal(out.topk_idx.cpu(), want_idx)
+    torch.testing.assert_close(out.topk_val.cpu(), want_val, rtol=0, atol=0)
+
+
 # ---- edge cases of the domain -----------------------------------------------------------
 def test_empty_query_batch(mcl):
     _, t = make_inputs(1, 500, 64, 80)

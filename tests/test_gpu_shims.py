@@ -190,6 +190,31 @@ def test_f1_lm_head_shim_trains_the_table():
     assert not ev.loss.requires_grad
 
 
+def test_host_query_pipeline_reused_results_live_lag_plus_one_yields():
+    """with reuse_host_buffers=True the results rotate through 2*lag + 2 pinned sets; a
+    yielded result must stay intact until lag + 1 MORE results have been yielded (no copy may land
+    in it earlier).  Every result is held un-cloned next to a clone and compared after lag + 1
+    further yields, with batches that all give different answers."""
+    from multimodal_concept_learning_b200.pipeline import HostQueryPipeline
+    g = torch.Generator().manual_seed(71)
+    table = torch.randn(4000, 64, generator=g).to(torch.bfloat16).cuda()
+    batches = [torch.randn(150, 64, generator=g).to(torch.bfloat16).pin_memory() for _ in range(14)]
+    lag = 2
+    pipe = HostQueryPipeline(table, 10, scale=10.0, lag=lag, reuse_host_buffers=True)
+    held = []                                             # (live tensors, clones) in yield order
+    checked = 0
+    for res in pipe.run(batches):
+        held.append((res, tuple(t.clone() for t in res)))
+        if len(held) > lag + 1:
+            live, snap = held[len(held) - 1 - (lag + 1)]  # lag + 1 results have been yielded since
+            torch.cuda.synchronize()                      # any copy that could touch it has landed
+            for a, b in zip(live, snap):
+                assert torch.equal(a, b), "a reused host buffer was overwritten inside its documented lifetime"
+            checked += 1
+    assert checked == len(batches) - (lag + 1)
+    assert not torch.equal(held[0][1][1], held[1][1][1])  # the batches really differ
+
+
 @pytest.mark.parametrize("reuse", [False, True])
 def test_host_query_pipeline_matches_direct_scan(reuse):
     """Fresh pinned results per batch, or a ring of lag + 2 reused result sets (each result is
