@@ -303,7 +303,9 @@ int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtyp
  *                       each is mcl_sharded_p2p_block_bytes(Q, k, world) bytes from mcl_peer_alloc
  *                       (zeroed), the others' opened with mcl_peer_open.  One set of blocks serves
  *                       one (Q, k) shape; `epoch` counts the scans issued on it: 1, 2, 3, ...  (the
- *                       same on every rank -- the arrival counters are monotone).
+ *                       same on every rank -- the arrival counters are monotone); `full_epoch`
+ *                       counts those of them that ran WITHOUT MCL_SHARDED_LOCAL_ROWS, this one
+ *                       included (the merged rows travel, and their counter advances, only then).
  *   mcl_sharded_p2p_block_bytes returns 0 when the shape cannot take this path (it needs
  *                       2 <= world <= 16, Q % world == 0 and (Q / world) * k % 4 == 0): use
  *                       mcl_concept_scan_sharded_ex then.
@@ -316,8 +318,8 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
                                  int k, int64_t index_base, const int64_t* labels,
                                  float* topk_val, int64_t* topk_idx, float* row_stats,
                                  void* workspace, size_t workspace_bytes, void* const* peer_blocks,
-                                 size_t block_bytes, int world, int rank, uint32_t epoch, int flags,
-                                 mcl_stream_t stream);
+                                 size_t block_bytes, int world, int rank, uint32_t epoch,
+                                 uint32_t full_epoch, int flags, mcl_stream_t stream);
 
 /*
  * Peer exchange of replicated query batches without SMs.  A sharded scan needs the whole query

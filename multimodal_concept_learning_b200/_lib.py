@@ -72,7 +72,7 @@ SIGNATURES = {
     "mcl_sharded_p2p_block_bytes": (_sz, [_i64, _i32, _i32]),
     "mcl_concept_scan_sharded_p2p": (_i32, [_ptr, _ptr, _i32, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr,
                                             _f32, _i32, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _sz,
-                                            C.POINTER(_ptr), _sz, _i32, _i32, C.c_uint32, _i32, _ptr]),
+                                            C.POINTER(_ptr), _sz, _i32, _i32, C.c_uint32, C.c_uint32, _i32, _ptr]),
     "mcl_peer_alloc": (_i32, [_sz, C.POINTER(_ptr), _ptr]),
     "mcl_peer_free": (_i32, [_ptr]),
     "mcl_peer_open": (_i32, [_ptr, C.POINTER(_ptr)]),

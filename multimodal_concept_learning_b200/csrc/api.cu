@@ -863,7 +863,8 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
                                  int64_t index_base, const int64_t* labels, float* topk_val,
                                  int64_t* topk_idx, float* row_stats, void* workspace,
                                  size_t workspace_bytes, void* const* peer_blocks, size_t block_bytes,
-                                 int world, int rank, uint32_t epoch, int flags, mcl_stream_t stream) {
+                                 int world, int rank, uint32_t epoch, uint32_t full_epoch, int flags,
+                                 mcl_stream_t stream) {
   if (world < 2 || world > kPushMaxPeers || rank < 0 || rank >= world) return fail(MCL_ERR_BAD_ARG, "bad world/rank");
   if (index_base < 0 || index_base + V_local > (1ll << 32))
     return fail(MCL_ERR_BAD_ARG, "global table rows must stay below 2^32 (index_base %lld + V_local %lld)",
@@ -874,6 +875,9 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
   for (int r = 0; r < world; ++r)
     if (!peer_blocks[r] || !aligned16(peer_blocks[r])) return fail(MCL_ERR_BAD_ARG, "null / unaligned peer block %d", r);
   if (epoch == 0) return fail(MCL_ERR_BAD_ARG, "epoch counts the scans on these blocks from 1");
+  if (!(flags & MCL_SHARDED_LOCAL_ROWS) && (full_epoch == 0 || full_epoch > epoch))
+    return fail(MCL_ERR_BAD_ARG, "full_epoch counts the scans without MCL_SHARDED_LOCAL_ROWS on these blocks from 1 "
+                "(this one included): the second arrival counter advances only in those");
   cu_wait32_t wait32 = get_wait32();
   if (!wait32) return fail(MCL_ERR_UNIMPLEMENTED, "cuStreamWaitValue32 is not available in this driver");
   DevInfo di;
@@ -962,7 +966,7 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
   e = launch_p2p_push(pf, di.sm, s);
   if (e != cudaSuccess) return cuda_fail(e, "p2p push launch (merged rows)");
   g_launches++;
-  wrc = wait32(s, (unsigned long long)(uintptr_t)(me + L.fcount), epoch * (uint32_t)(world - 1), /*GEQ*/ 0u);
+  wrc = wait32(s, (unsigned long long)(uintptr_t)(me + L.fcount), full_epoch * (uint32_t)(world - 1), /*GEQ*/ 0u);
   if (wrc) return fail(MCL_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", wrc);
   // 6. hand the result to the caller's arrays
   e = copy_out(fin + rec.val_off, (char*)topk_val, (size_t)Q * k * 4, fin + rec.idx_off, (char*)topk_idx,

@@ -146,7 +146,7 @@ class ShardedConceptScan:
                     check(lib.mcl_peer_open(h, C.byref(pp)))
                     ptrs[r] = pp.value
         dist.barrier(group=self.group)              # every mapping exists before the first store
-        board = {"base": ptr.value, "ptrs": ptrs, "bytes": nbytes, "epoch": 0,
+        board = {"base": ptr.value, "ptrs": ptrs, "bytes": nbytes, "epoch": 0, "full_epoch": 0,
                  "array": (C.c_void_p * self.world)(*ptrs)}
         self._boards[key] = board
         return board
@@ -214,6 +214,8 @@ class ShardedConceptScan:
         board = self._p2p_board(Q, kk)
         if board is not None:
             board["epoch"] += 1
+            if not local_rows_only:                  # the merged rows travel (and are counted) only then
+                board["full_epoch"] += 1
             with torch.cuda.device(dev):
                 ws_bytes = lib.mcl_scan_workspace_bytes(Q, self.hi - self.lo, D, kk, code)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -222,7 +224,7 @@ class ShardedConceptScan:
                     self.table.stride(0), ops._ptr(inv_norm_q), ops._ptr(self.inv_norm_t), float(scale),
                     kk, self.lo, ops._ptr(labels), val.data_ptr(), idx.data_ptr(), stats.data_ptr(),
                     ws.data_ptr(), ws_bytes, board["array"], board["bytes"], self.world, self.rank,
-                    board["epoch"], flags, ops._stream(dev)))
+                    board["epoch"], board["full_epoch"], flags, ops._stream(dev)))
             return ops.ScanOutput(val, idx, stats, self.vocab_total, labels, float(label_smoothing))
         with torch.cuda.device(dev):
             gbytes = lib.mcl_sharded_gather_bytes(Q, kk, self.world)

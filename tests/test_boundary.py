@@ -100,7 +100,7 @@ def test_host_only_sizing_of_the_round2_entry_points(lib_built):
     blocks = (C.c_void_p * 2)(p16, p16)
     def p2p(world=2, rank=0, epoch=1, Q=304, block_bytes=1 << 30, k=50):
         return lib.mcl_concept_scan_sharded_p2p(p16, p16, 0, Q, 3000, 64, 64, 64, None, None, 1.0, k, 0, None, p16, p16,
-                                                p16, p16, 4096, blocks, block_bytes, world, rank, epoch, 0, None)
+                                                p16, p16, 4096, blocks, block_bytes, world, rank, epoch, epoch, 0, None)
     assert p2p(world=1) == -1 and p2p(rank=2) == -1
     assert p2p(Q=301) == -1 and "Q % world" in _lib.last_error()
     assert p2p(block_bytes=64) == -4                                  # MCL_ERR_WORKSPACE_TOO_SMALL

@@ -82,6 +82,16 @@ def _worker(rank, world, port, ret, exchange="auto"):
             want_val = full.topk_val.cpu() if i % 2 == 0 else full.topk_val.cpu().flip(0)
             assert torch.equal(ix, want_idx[r0:r1]) and torch.equal(v, want_val[r0:r1]), f"batch {i}"
         pipe.close()
+        # full scans after scans that kept only the local rows, on the same peer blocks: the two arrival
+        # counters of the peer-memory exchange advance at different rates
+        for _ in range(2):
+            again = sc.scan(qd, k, scale=20.0, labels=ld, label_smoothing=0.1)
+        part = sc.scan(qd, k, scale=20.0, labels=ld, local_rows_only=True)
+        last = sc.scan(qd, k, scale=20.0, labels=ld, label_smoothing=0.1)
+        torch.cuda.synchronize()
+        assert torch.equal(again.topk_idx, full.topk_idx) and torch.equal(last.topk_val, full.topk_val)
+        p0, p1 = sc.local_rows_for(304, k)
+        assert torch.equal(part.topk_idx[p0:p1], full.topk_idx[p0:p1])
         sc.close()
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
