@@ -718,7 +718,14 @@ cudaError_t launch_panel_scan(const ScanArgs& a, int sm_count, float* scores, in
   p.scores = scores; p.ld = ld;
   p.gmax = gmax; p.gld = gld; p.part = (float4*)part;
   p.topk_val = topk_val; p.topk_idx = (long long*)topk_idx; p.row_stats = (float4*)row_stats;
-  p.sync = g_pn_sync[dev] + 16 * (g_pn_next.fetch_add(1) % 64);
+  // pairs 0..31 rotate over direct launches, 32..63 over launches recorded into CUDA graphs (a graph
+  // keeps its pair for life: it must not meet a direct launch on another stream in the same pair)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  static std::atomic<unsigned> next_captured{0};
+  const unsigned pair = cap == cudaStreamCaptureStatusActive ? 32u + next_captured.fetch_add(1) % 32u
+                                                             : g_pn_next.fetch_add(1) % 32u;
+  p.sync = g_pn_sync[dev] + 16 * pair;
   p.fault = g_pn_fault[dev];
   p.timing = (unsigned long long*)a.timing;
   const int grid = std::min(sm_count, (int)((a.V + 31) / 32));   // every CTA owns at least one group of 32 rows
