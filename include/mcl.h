@@ -302,8 +302,9 @@ int mcl_concept_scan_sharded_ex(const void* q, const void* table_shard, int dtyp
  *   peer_blocks[world]  HOST array of device pointers: block r is rank r's (own block at [rank]);
  *                       each is mcl_sharded_p2p_block_bytes(Q, k, world) bytes from mcl_peer_alloc
  *                       (zeroed), the others' opened with mcl_peer_open.  One set of blocks serves
- *                       one (Q, k) shape; `epoch` counts the scans issued on it: 1, 2, 3, ...  (the
- *                       same on every rank -- the arrival counters are monotone); `full_epoch`
+ *                       one (Q, k) shape; `epoch` counts the scans issued on it: 1, 2, 3, ... up to
+ *                       2^31 (the same on every rank -- the arrival counters are monotone and, like
+ *                       the receive areas, alternate with the epoch's parity); `full_epoch`
  *                       counts those of them that ran WITHOUT MCL_SHARDED_LOCAL_ROWS, this one
  *                       included (the merged rows travel, and their counter advances, only then).
  *   mcl_sharded_p2p_block_bytes returns 0 when the shape cannot take this path (it needs

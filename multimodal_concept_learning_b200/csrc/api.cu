@@ -874,7 +874,8 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
   if (!peer_blocks || block_bytes < need) return fail(MCL_ERR_WORKSPACE_TOO_SMALL, "peer block %zu B < required %zu B", block_bytes, need);
   for (int r = 0; r < world; ++r)
     if (!peer_blocks[r] || !aligned16(peer_blocks[r])) return fail(MCL_ERR_BAD_ARG, "null / unaligned peer block %d", r);
-  if (epoch == 0) return fail(MCL_ERR_BAD_ARG, "epoch counts the scans on these blocks from 1");
+  if (epoch == 0 || epoch > (1u << 31))
+    return fail(MCL_ERR_BAD_ARG, "epoch counts the scans on these blocks from 1 (at most 2^31: take fresh blocks then)");
   if (!(flags & MCL_SHARDED_LOCAL_ROWS) && (full_epoch == 0 || full_epoch > epoch))
     return fail(MCL_ERR_BAD_ARG, "full_epoch counts the scans without MCL_SHARDED_LOCAL_ROWS on these blocks from 1 "
                 "(this one included): the second arrival counter advances only in those");
@@ -902,8 +903,14 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
   // rank wait for a slow one, but its push of step e+2 needs the slow rank's push of step e+1, which
   // follows that rank's merge of step e in stream order -- so the area of step e is free by then.
   const size_t xin_off = L.xin + (size_t)(epoch & 1u) * mini.bytes * (size_t)world;
+  // The arrival counters alternate with the epoch like the areas: a peer can run at most ONE step
+  // ahead of this rank's wait (same argument), so counter [e & 1] only ever holds arrivals of steps
+  // e, e-2, ...: reaching its target proves that every peer's pieces of step e are here, never that
+  // a fast peer's pieces of step e+1 made up for a slow peer's of step e.
+  const size_t xcount_off = L.xcount + 4u * (size_t)(epoch & 1u);
+  const uint32_t xcount_target = ((epoch + 1u) >> 1) * (uint32_t)(world - 1);   // steps of this parity so far
   PushParams pp{};
-  pp.npeer = world; pp.self = rank; pp.counter_off = L.xcount; pp.done = (unsigned*)(me + L.done);
+  pp.npeer = world; pp.self = rank; pp.counter_off = xcount_off; pp.done = (unsigned*)(me + L.done);
   for (int r = 0; r < world; ++r) pp.peer[r] = (char*)peer_blocks[r];
   for (int peer = 0; peer < world; ++peer) {
     const size_t r0 = (size_t)peer * rows, slot = xin_off + mini.bytes * (size_t)rank;
@@ -916,7 +923,7 @@ int mcl_concept_scan_sharded_p2p(const void* q, const void* table_shard, int dty
   if (e != cudaSuccess) return cuda_fail(e, "p2p push launch");
   g_launches++;
   // 3. wait for the other ranks' pieces (a stream memory operation: no SM spins)
-  int wrc = wait32(s, (unsigned long long)(uintptr_t)(me + L.xcount), epoch * (uint32_t)(world - 1), /*GEQ*/ 0u);
+  int wrc = wait32(s, (unsigned long long)(uintptr_t)(me + xcount_off), xcount_target, /*GEQ*/ 0u);
   if (wrc) return fail(MCL_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult %d", wrc);
   // 4. merge my rows into their place in the result area
   char* fin = me + L.fin;

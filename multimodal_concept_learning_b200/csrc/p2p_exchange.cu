@@ -16,7 +16,12 @@
 // Reuse of the areas needs no extra handshake: a rank enters step e+1 only after it has seen
 // every peer's merged rows of step e, and a peer sends those only after its own merge of step e has
 // read its receive area; a peer's merged rows of step e+1 need this rank's push of step e+1, which
-// follows this rank's copy-out of step e in stream order.
+// follows this rank's copy-out of step e in stream order.  When push 2 is skipped (the caller takes
+// only the rows it merged) nothing after the merge holds a fast rank back, but its push 1 of step
+// e+2 still needs every peer's push 1 of step e+1, which follows that peer's merge of step e: a
+// rank runs at most ONE step ahead of any peer's wait.  The receive areas AND the arrival counters
+// of push 1 therefore alternate with the step's parity (api.cu): counter [e & 1] holds arrivals of
+// steps e, e-2, ... only, so reaching its target means that all pieces of step e have landed.
 #include "kernels.h"
 
 namespace mcl {

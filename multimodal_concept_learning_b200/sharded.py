@@ -2,12 +2,17 @@
 
 One process per GPU (``torch.distributed``; backend ``nccl`` on the box).  Rank r holds
 table rows ``[r*ceil(V/N), min(V, (r+1)*ceil(V/N)))``; queries are replicated.  Every scan is
-three operations enqueued on torch's current stream by ONE C call
-(``mcl_concept_scan_sharded``): the local fused scan, a single ``ncclAllGather`` of the packed
-per-rank record ``(k values, k indices, m, s, sum_z, z_label)`` per query -- Q*(12k+16) bytes
-per rank, latency-bound on NVLink 5 -- and the merge kernel.  ``torch.distributed`` is used
-for plumbing only: it carries the 128-byte ``ncclUniqueId`` of the library's private
-communicator from rank 0 to the others (torch does not expose its own ``ncclComm_t``)."""
+ONE C call that enqueues, on torch's current stream, the local fused scan, the exchange of the
+per-rank records ``(k values, k indices, m, s, sum_z, z_label)`` per query -- rank j collects and
+merges query rows ``[j*Q/N, (j+1)*Q/N)`` -- and the distribution of the merged rows:
+
+* ``mcl_concept_scan_sharded_p2p`` (default): stores into the peers' memory over NVLink, arrival
+  counters, stream waits; no NCCL call in the step (``csrc/p2p_exchange.cu``);
+* ``mcl_concept_scan_sharded_ex`` (``exchange="nccl"``, and whenever the shape rules the peer-memory
+  path out): one ``ncclAllGather`` + full merge at world 2, grouped send/recv + all-gather above.
+
+``torch.distributed`` is plumbing only: it carries the 128-byte ``ncclUniqueId`` of the library's
+private communicator and the CUDA IPC handles of the peer-memory blocks between the ranks."""
 from __future__ import annotations
 
 import ctypes as C
@@ -55,8 +60,10 @@ def _nccl_unique_id() -> bytes:
 
 
 class ShardedConceptScan:
-    """Holds this rank's table shard, its cached inverse norms, the private NCCL communicator
-    and the reusable gather buffer."""
+    """Holds this rank's table shard, its cached inverse norms, the private NCCL communicator,
+    the peer-memory blocks of the result exchange and the reusable gather buffer."""
+
+    MAX_EPOCH = 1 << 31               # scans per set of peer-memory blocks (include/mcl.h)
 
     def __init__(self, table_shard: Tensor, vocab_total: int, *, normalize_t: bool = True,
                  group=None, exchange: str = "auto"):
@@ -98,18 +105,29 @@ class ShardedConceptScan:
             with torch.cuda.device(self.device):
                 check(load().mcl_comm_init(uid, self.world, self.rank, C.byref(self._comm)))
 
+    def _free_boards(self, boards) -> None:
+        """Collective: every rank frees the same boards.  Order required by CUDA IPC: all stores
+        have landed, every importer has closed its mapping, only then does the owner free."""
+        lib = load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)              # nobody stores into a block that is being freed
+        with torch.cuda.device(self.device):
+            for board in boards:
+                for r, p in enumerate(board["ptrs"]):
+                    if r != self.rank and p:
+                        lib.mcl_peer_close(p)
+        dist.barrier(group=self.group)              # no mapping of a block is left when its owner frees it
+        with torch.cuda.device(self.device):
+            for board in boards:
+                lib.mcl_peer_free(board["base"])
+
     def close(self):
+        """Frees the peer-memory blocks and the communicator.  A COLLECTIVE when the peer-memory
+        exchange was used: call it on every rank (garbage collection does not do it for you -- a
+        finaliser must not enter a barrier)."""
         if getattr(self, "_boards", None):
-            lib = load()
-            torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)          # nobody stores into a block that is being freed
-            with torch.cuda.device(self.device):
-                for board in self._boards.values():
-                    for r, p in enumerate(board["ptrs"]):
-                        if r != self.rank and p:
-                            lib.mcl_peer_close(p)
-                    lib.mcl_peer_free(board["base"])
-            self._boards = {}
+            boards, self._boards = list(self._boards.values()), {}
+            self._free_boards(boards)
         if self._comm:
             check(load().mcl_comm_destroy(self._comm))
             self._comm = C.c_void_p(None)
@@ -122,6 +140,11 @@ class ShardedConceptScan:
             return None
         key = (int(Q), int(k))
         board = self._boards.get(key)
+        if board is not None and board["epoch"] >= self.MAX_EPOCH:
+            # the library counts the scans on a set of blocks in 32 bits: start over on fresh blocks
+            # (every rank gets here in the same scan: the epochs advance in lockstep)
+            self._free_boards([self._boards.pop(key)])
+            board = None
         if board is not None:
             return board
         lib = load()
@@ -152,7 +175,14 @@ class ShardedConceptScan:
         return board
 
     def __del__(self):
+        # never a collective from a finaliser (the ranks collect garbage at different times): the
+        # peer-memory blocks of an unclosed scanner are left to process exit
         try:
+            if getattr(self, "_boards", None):
+                import warnings
+                warnings.warn("ShardedConceptScan dropped without close(): its peer-memory blocks stay "
+                              "allocated until the process exits", ResourceWarning)
+                return
             self.close()
         except Exception:
             pass
@@ -350,6 +380,8 @@ class QueryBoard:
             for r, p in enumerate(self.peer_base):
                 if r != self.rank and p:
                     lib.mcl_peer_close(p)
+        dist.barrier(group=self.scanner.group)      # every importer closed its mapping before the owner frees
+        with torch.cuda.device(self.device):
             self.batches = []
             lib.mcl_peer_free(self.base)
         self.base = None
