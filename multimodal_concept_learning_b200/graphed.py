@@ -2,11 +2,12 @@
 
 The reference's own workloads score a handful of concept tokens (16-96 rows,
 `token_embedding_analysis.py:183-260`) against the vocabulary table.  At that size one scan is
-~20 us of GPU work behind ~100 us of host work (op dispatch, output allocation, five kernel
-launches), so the step is launch-bound.  Capturing the whole step -- row norms of the queries,
-threshold clear, tcgen05 scan, slot merge -- once and replaying it removes the host from the
-loop: one `cudaGraphLaunch` per step.  The kernels and their results are the ones
-:func:`concept_scan` runs; only the launch mechanism differs.
+~27 us of GPU work (ONE launch: `panel_scan_kernel`, csrc/panel_scan.cu; plus `ce_from_stats`
+when labels are given) behind the host work of a call -- argument checks, output allocation, the
+launch itself --, so the step is launch-bound: 35 us per direct call on a B200.  Capturing the
+step once and replaying it takes the host out of the loop: one `cudaGraphLaunch` per step (larger
+batches replay their row-norm / seed / scan / merge launches the same way).  The kernels and
+their results are the ones :func:`concept_scan` runs; only the launch mechanism differs.
 """
 from __future__ import annotations
 
