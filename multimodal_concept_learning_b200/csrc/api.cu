@@ -663,7 +663,10 @@ int mcl_gemm_bf16(const void* a, int a_mn, int64_t lda, const void* b, int b_mn,
 
 int mcl_comm_unique_id(void* unique_id_out) {
   NcclApi* n = nccl();
-  if (!n) return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror() ? dlerror() : "");
+  if (!n) {
+    const char* why = dlerror();                     // (one call: dlerror() clears what it returns)
+    return fail(MCL_ERR_NCCL, "libnccl.so.2 not loadable: %s", why ? why : "");
+  }
   if (!unique_id_out) return fail(MCL_ERR_BAD_ARG, "null pointer");
   int rc = n->get_uid((NcclUid*)unique_id_out);
   if (rc) return nccl_fail(n, rc, "ncclGetUniqueId");
