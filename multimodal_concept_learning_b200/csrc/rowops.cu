@@ -213,6 +213,10 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 // whenever nothing under- or overflows; outside that range the true division is taken (a warp
 // vote, practically never).  Bit-identical to x / n: tests compare with the register kernels,
 // which divide, and oracle/check_div_identity.py samples the identity on the host for n = 1 .. 1000.
+#ifndef MCL_GM_UNROLL
+#define MCL_GM_UNROLL 1   // column-loop unroll of the ring path (1, 2 and 4 measured: profiles/README.md)
+#endif
+constexpr int kGmUnroll = MCL_GM_UNROLL;
 template <typename T, int NV>
 __global__ void __launch_bounds__(NV > 8 ? 256 : 512, 1)
 gather_mean_bulk_kernel(const T* __restrict__ table, long long V, int D, long long ld,
@@ -295,7 +299,7 @@ gather_mean_bulk_kernel(const T* __restrict__ table, long long V, int D, long lo
       const uint32_t s_b = slot0 + (cs + 1 == (uint32_t)S ? 0u : cs + 1) * slot_stride;
       for (int pass = normalize ? 0 : 1; pass < 2; ++pass) {
         float ss = 0.f;
-#pragma unroll 1
+#pragma unroll kGmUnroll
         for (int i = 0; i < nvl; ++i) {
           const int v = lane + 32 * i;
           float acc[N];
