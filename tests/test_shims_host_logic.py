@@ -122,3 +122,27 @@ def test_shims_refuse_to_compute_without_a_gpu():
     from multimodal_concept_learning_b200.shims.vision_training import classifier_loss_and_top1
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         classifier_loss_and_top1(torch.randn(4, 16), torch.randn(10, 16), torch.zeros(10), torch.tensor([1, 2, 3, 4]))
+
+
+def test_lazy_logits_surface_and_dispatch_without_touching_the_operands():
+    """``outputs.logits`` under the fused forwards: tensor-like shape / dtype / ``.data`` without any
+    computation; the three reads the reference makes (argmax, max(.,1), cross_entropy) are routed to
+    the fused scan -- on a machine without a GPU they must raise, not fall back to a dense matmul."""
+    from multimodal_concept_learning_b200.shims.lazy_logits import LazyLogits
+    f = torch.randn(2, 5, 16).to(torch.bfloat16)
+    w = torch.randn(40, 16).to(torch.bfloat16)
+    lazy = LazyLogits(f, w)
+    assert lazy.shape == torch.Size((2, 5, 40)) and lazy.size(-1) == 40 and lazy.dim() == 3 and len(lazy) == 2
+    assert lazy.dtype == torch.bfloat16 and lazy.device == f.device
+    assert lazy.data is lazy and lazy.detach() is lazy and lazy._dense is None
+    assert "materialized=False" in repr(lazy)
+    if NO_GPU:
+        for read in (lambda: torch.argmax(lazy, dim=-1), lambda: torch.max(lazy.data, 2),
+                     lambda: LazyLogits(f[0], w).cross_entropy(torch.tensor([1, 2, 3, 4, 5]))):
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                read()
+        assert lazy._dense is None, "a refused fused read must not have materialised the logits"
+    # any OTHER use is the reference's own expression (nn.Linear), computed once and cached
+    dense = lazy.float()
+    torch.testing.assert_close(dense, (f.float() @ w.float().T).to(torch.bfloat16).float(), rtol=2e-2, atol=2e-2)
+    assert lazy._dense is not None and lazy[0].shape == (5, 40)
