@@ -1,93 +1,136 @@
 """Model check of the arrival-counter protocol of the peer-memory result exchange
-(csrc/p2p_exchange.cu, api.cu::mcl_concept_scan_sharded_p2p) in its hardest mode: every rank
-takes only the rows it merged (MCL_SHARDED_LOCAL_ROWS), so nothing after the merge holds a fast
-rank back.
+(csrc/p2p_exchange.cu, api.cu::mcl_concept_scan_sharded_p2p).
 
-Per step e = 1, 2, ... a rank (stream order)  pushes its pieces into every peer's receive area
-[e & 1] and bumps that peer's counter -- one delivery per destination, each arbitrarily late --,
-waits for its own counter to reach a target, then merges area [e & 1] (which must hold every
-peer's pieces of step e, nothing older, nothing newer).
+Per step e = 1, 2, ... every rank executes, in stream order,
+    push 1   its pieces into every peer's receive area [e & 1] + a bump of that peer's counter
+             (one delivery per destination, each arbitrarily late: stores, fence, then the atomic),
+    wait x   for its own counter to reach a target,
+    merge    of receive area [e & 1] -- which must hold every peer's pieces of step e,
+and, unless the step keeps only the rows the rank merged itself (MCL_SHARDED_LOCAL_ROWS),
+    push 2   the merged rows into every peer's result area + a bump of the peer's second counter,
+    wait f   for the second counter (monotone, counts the full steps),
+    copy     of the result area -- which must hold every peer's merged rows of step e.
+All ranks run the same sequence of full / local steps.
 
-The library's scheme -- counters alternating with the step's parity, target = steps of that parity
-so far * (world - 1) -- must be safe under EVERY schedule; a single monotone counter (the first
-implementation) is not: a fast peer's arrival of step e+1 can stand in for a slow peer's of step e.
-Random adversarial schedules find that hole within a few hundred runs, which is what shows the
-model is sharp enough to mean something when it passes.  No GPU needed."""
+What is checked under random adversarial schedules (deliveries as late as the waits allow):
+  * a merge / copy never reads pieces of another step (stale or newer),
+  * no delivery overwrites pieces that their reader has not consumed yet,
+  * nothing deadlocks.
+The library's scheme for push 1 -- counters alternating with the step's parity, target = steps of
+that parity so far * (world - 1) -- must pass; a single monotone counter (the first
+implementation) must NOT: with local steps a fast peer's arrival of step e+1 can stand in for a
+slow peer's of step e.  That the model finds that hole within a few hundred schedules is what shows
+it is sharp enough to mean something when it passes.  No GPU needed."""
 import random
 
 import pytest
 
 
-def run_schedule(world, steps, rng, parity_counters):
-    """One random schedule.  Returns the first violation as a string, or None."""
+def run_schedule(world, modes, rng, parity_counters):
+    """One random schedule of len(modes) steps (modes[e-1] = True: full step).  Returns the first
+    violation as a string, or None."""
+    steps = len(modes)
     n_ctr = 2 if parity_counters else 1
-    counter = [[0] * n_ctr for _ in range(world)]
-    # area[r][parity][src] = step whose pieces of `src` lie in rank r's receive area
-    area = [[[0] * world for _ in range(2)] for _ in range(world)]
-    in_flight = []                       # (dst, src, step): stores + bump of one destination, not yet landed
-    pc = [("push", 1)] * world           # next action of every rank
+    xcount = [[0] * n_ctr for _ in range(world)]
+    fcount = [0] * world
+    # xin[r][parity][src] / fin[r][src] = step whose pieces of `src` lie in rank r's areas
+    xin = [[[0] * world for _ in range(2)] for _ in range(world)]
+    fin = [[0] * world for _ in range(world)]
+    merged = [0] * world                 # last step whose receive area the rank has read
+    copied = [0] * world                 # last FULL step whose result area the rank has read
+    fulls_upto = [0] * (steps + 1)       # number of full steps among 1..e
+    for e in range(1, steps + 1):
+        fulls_upto[e] = fulls_upto[e - 1] + (1 if modes[e - 1] else 0)
+    prev_full = [0] * (steps + 1)        # last full step before e
+    for e in range(1, steps + 1):
+        prev_full[e] = e - 1 if (e > 1 and modes[e - 2]) else (prev_full[e - 1] if e > 1 else 0)
+    in_flight = []                       # (phase, dst, src, step): stores + bump of one destination, not landed
+    pc = [("push1", 1)] * world          # next action of every rank
     done = [False] * world
+
+    def ready(r):
+        kind, e = pc[r]
+        if kind in ("push1", "push2"):
+            return True
+        if kind == "merge":
+            c = (e & 1) if parity_counters else 0
+            target = ((e + 1) >> 1) * (world - 1) if parity_counters else e * (world - 1)
+            return xcount[r][c] >= target
+        return fcount[r] >= fulls_upto[e] * (world - 1)          # "copy"
+
     while not all(done) or in_flight:
-        moves = [("deliver", i) for i in range(len(in_flight))]
-        for r in range(world):
-            if done[r]:
-                continue
-            kind, e = pc[r]
-            if kind == "push":
-                moves.append(("rank", r))
-            else:
-                c = (e & 1) if parity_counters else 0
-                target = ((e + 1) >> 1) * (world - 1) if parity_counters else e * (world - 1)
-                if counter[r][c] >= target:
-                    moves.append(("rank", r))
-        if not moves:
+        ranks = [r for r in range(world) if not done[r] and ready(r)]
+        if not ranks and not in_flight:
             return "deadlock"
         # adversary: deliveries are lazy, so that ranks run ahead of their peers' stores
-        ranks = [m for m in moves if m[0] == "rank"]
-        kind, x = rng.choice(ranks) if ranks and rng.random() < 0.8 else rng.choice(moves)
-        if kind == "deliver":
-            dst, src, e = in_flight.pop(x)
-            if area[dst][e & 1][src] > e:
-                return f"rank {dst}: pieces of step {e} from {src} overwrote newer ones"
-            area[dst][e & 1][src] = e            # the data lands, THEN the counter moves (fence + atomic)
-            counter[dst][(e & 1) if parity_counters else 0] += 1
-            continue
-        r = x
-        kind, e = pc[r]
-        if kind == "push":
-            for dst in range(world):
-                if dst != r:
-                    in_flight.append((dst, r, e))
-            pc[r] = ("merge", e)
-        else:                                    # the wait was satisfied: merge area [e & 1]
-            for src in range(world):
-                if src != r and area[r][e & 1][src] != e:
-                    return (f"rank {r} merged step {e} with pieces of step {area[r][e & 1][src]} "
-                            f"from rank {src}")
-            if e == steps:
-                done[r] = True
+        if ranks and (not in_flight or rng.random() < 0.8):
+            r = rng.choice(ranks)
+            kind, e = pc[r]
+            if kind == "push1":
+                in_flight += [("x", dst, r, e) for dst in range(world) if dst != r]
+                pc[r] = ("merge", e)
+            elif kind == "merge":
+                for src in range(world):
+                    if src != r and xin[r][e & 1][src] != e:
+                        return f"rank {r} merged step {e} with pieces of step {xin[r][e & 1][src]} from rank {src}"
+                merged[r] = e
+                pc[r] = ("push2", e) if modes[e - 1] else ("push1", e + 1)
+                if not modes[e - 1] and e == steps:
+                    done[r] = True
+            elif kind == "push2":
+                in_flight += [("f", dst, r, e) for dst in range(world) if dst != r]
+                pc[r] = ("copy", e)
             else:
-                pc[r] = ("push", e + 1)
+                for src in range(world):
+                    if src != r and fin[r][src] != e:
+                        return f"rank {r} copied step {e} with merged rows of step {fin[r][src]} from rank {src}"
+                copied[r] = e
+                pc[r] = ("push1", e + 1)
+                if e == steps:
+                    done[r] = True
+            continue
+        phase, dst, src, e = in_flight.pop(rng.randrange(len(in_flight)))
+        if phase == "x":
+            if e - 2 > merged[dst]:
+                return f"rank {dst}: pieces of step {e} from {src} overwrote step {e - 2} before it was merged"
+            xin[dst][e & 1][src] = e             # the data lands, THEN the counter moves (fence + atomic)
+            xcount[dst][(e & 1) if parity_counters else 0] += 1
+        else:
+            if prev_full[e] > copied[dst]:
+                return f"rank {dst}: merged rows of step {e} from {src} overwrote step {prev_full[e]} before the copy"
+            fin[dst][src] = e
+            fcount[dst] += 1
     return None
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_parity_counters_are_safe_under_random_schedules(world):
+@pytest.mark.parametrize("kind", ["local", "full", "mixed"])
+def test_parity_counters_are_safe_under_random_schedules(world, kind):
     rng = random.Random(1000 + world)
-    for _ in range(400):
-        assert run_schedule(world, steps=6, rng=rng, parity_counters=True) is None
+    for i in range(250):
+        modes = {"local": [False] * 6, "full": [True] * 6,
+                 "mixed": [rng.random() < 0.5 for _ in range(7)]}[kind]
+        assert run_schedule(world, modes, rng, parity_counters=True) is None, (i, modes)
 
 
 def test_single_counter_is_not():
-    """The model finds the race of a single monotone counter (three or more ranks: with two the
-    only peer's arrivals come in order)."""
+    """The model finds the race of a single monotone counter in local-rows mode (three or more
+    ranks: with two the only peer's arrivals come in order)."""
     rng = random.Random(7)
     found = None
     for _ in range(3000):
-        found = run_schedule(4, steps=6, rng=rng, parity_counters=False)
+        found = run_schedule(4, [False] * 6, rng, parity_counters=False)
         if found:
             break
     assert found and "merged step" in found
+
+
+def test_single_counter_suffices_when_every_step_is_full():
+    """... and only there: the second wait of a full step holds every rank back until all merged
+    rows have arrived, so no peer runs ahead -- which is why the SECOND counter may stay monotone."""
+    rng = random.Random(9)
+    for _ in range(300):
+        assert run_schedule(4, [True] * 5, rng, parity_counters=False) is None
 
 
 def test_targets_match_the_library_formula():
